@@ -1,0 +1,235 @@
+"""Keras-surface layers on the B200 kernels.
+
+`BidirectionalLSTM(F, H, dropout=p)` mirrors
+    Bidirectional(LSTM(H, activation='tanh', recurrent_activation='hard_sigmoid',
+                       recurrent_dropout=0.0, dropout=p, kernel_constraint=maxnorm(3),
+                       kernel_initializer=RandomUniform(-0.05, 0.05, seed=47),
+                       return_sequences=True), merge_mode='concat')
+(/root/reference/audio_network/speech_lstm_ctc_words.py:56-77, skeletal_network/
+skeletal_lstm_ctc.py:309-331, multimodal_fusion/multimodal.py:159-168): (B,T,F) -> (B,T,2H),
+`get_weights()/set_weights()` in Keras order [fwd kernel (F,4H), fwd recurrent (H,4H), fwd bias
+(4H), bwd kernel, bwd recurrent, bwd bias], gate order i,f,c,o, `.trainable` for freezing
+(multimodal.py:33-55).  `DenseSoftmax` mirrors Dense(C)+Activation('softmax') (speech:86-90).
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+
+GEMM_PASSES = 3  # bf16x3 (fp32-faithful) tensor-core projections; 1 = plain bf16
+
+
+def _project(x2, W, b, masks, B, T, H, passes):
+    """Hoisted input projection P = X W + b  -> (B*T, 8H), on tcgen05."""
+    BT, F = x2.shape
+    gates = torch.empty((BT, 8 * H), dtype=torch.float32, device=x2.device)
+    wt_hi, wt_lo = ops.split_bf16(W, transpose=True, want_lo=passes == 3)  # (8H, pad8(F))
+    Kp = wt_hi.shape[1]
+    if masks is None:
+        a_hi, a_lo = ops.split_bf16(x2, want_lo=passes == 3)
+        ops.gemm_nt(a_hi, a_lo, wt_hi, wt_lo, BT, 8 * H, Kp, out=gates, ldc=8 * H, bias=b, passes=passes)
+    else:
+        for dg in range(8):
+            n0 = dg * H
+            a_hi, a_lo = ops.split_bf16(x2, mask=masks[dg], rows_per_seq=T, want_lo=passes == 3)
+            ops.gemm_nt(a_hi, a_lo, wt_hi[n0:n0 + H], None if wt_lo is None else wt_lo[n0:n0 + H], BT, H, Kp,
+                        out=gates, ldc=8 * H, bias=b[n0:n0 + H], passes=passes, out_col_offset=n0)
+    return gates
+
+
+class _BlstmFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, U, b, masks, passes):
+        B, T, F = x.shape
+        H = U.shape[1]
+        x = x.contiguous()
+        x2 = x.reshape(B * T, F)
+        need_grad = any(ctx.needs_input_grad[:4])
+        gates = _project(x2, W, b, masks, B, T, H, passes)
+        y, cell = ops.lstm_recurrence_fwd(gates, U, B, T, H, keep_cell=need_grad)
+        if need_grad:
+            ctx.save_for_backward(x, W, U, masks, gates, cell, y)
+            ctx.passes = passes
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, U, masks, gates, cell, y = ctx.saved_tensors
+        passes = ctx.passes
+        B, T, F = x.shape
+        H = U.shape[1]
+        BT = B * T
+        lo = passes == 3
+        dP = ops.lstm_recurrence_bwd(gates, cell, dy.contiguous(), U, B, T, H).reshape(BT, 8 * H)
+        x2 = x.reshape(BT, F)
+        y2 = y.reshape(BT, 2 * H)
+        db = ops.colsum(dP) if ctx.needs_input_grad[3] else None
+        dW = dU = dx = None
+        dpt_hi, dpt_lo = ops.split_bf16(dP, transpose=True, want_lo=lo)  # (8H, pad8(BT))
+        Kbt = dpt_hi.shape[1]
+        if ctx.needs_input_grad[1]:
+            dW = torch.empty((F, 8 * H), dtype=torch.float32, device=x.device)
+            if masks is None:
+                xt_hi, xt_lo = ops.split_bf16(x2, transpose=True, want_lo=lo)
+                ops.gemm_nt(xt_hi, xt_lo, dpt_hi, dpt_lo, F, 8 * H, Kbt, out=dW, ldc=8 * H, passes=passes)
+            else:
+                for dg in range(8):
+                    n0 = dg * H
+                    xt_hi, xt_lo = ops.split_bf16(x2, mask=masks[dg], rows_per_seq=T, transpose=True, want_lo=lo)
+                    ops.gemm_nt(xt_hi, xt_lo, dpt_hi[n0:n0 + H], None if dpt_lo is None else dpt_lo[n0:n0 + H],
+                                F, H, Kbt, out=dW, ldc=8 * H, passes=passes, out_col_offset=n0)
+        if ctx.needs_input_grad[2]:
+            dU = torch.empty((2, H, 4 * H), dtype=torch.float32, device=x.device)
+            for d in range(2):
+                hp_hi, hp_lo = ops.split_bf16(y2, rows_per_seq=T, transpose=True, row_shift=-1 if d == 0 else 1,
+                                              ncols=H, col_offset=d * H, want_lo=lo)
+                ops.gemm_nt(hp_hi, hp_lo, dpt_hi[d * 4 * H:(d + 1) * 4 * H],
+                            None if dpt_lo is None else dpt_lo[d * 4 * H:(d + 1) * 4 * H], H, 4 * H, Kbt,
+                            out=dU[d], ldc=4 * H, passes=passes)
+        if ctx.needs_input_grad[0]:
+            dx2 = torch.empty((BT, F), dtype=torch.float32, device=x.device)
+            if masks is None:
+                dp_hi, dp_lo = ops.split_bf16(dP, want_lo=lo)
+                w_hi, w_lo = ops.split_bf16(W, want_lo=lo)
+                ops.gemm_nt(dp_hi, dp_lo, w_hi, w_lo, BT, F, dp_hi.shape[1], out=dx2, ldc=F, passes=passes)
+            else:
+                tmp = torch.empty((BT, F), dtype=torch.float32, device=x.device)
+                for dg in range(8):
+                    n0 = dg * H
+                    dp_hi, dp_lo = ops.split_bf16(dP, ncols=H, col_offset=n0, want_lo=lo)
+                    w_hi, w_lo = ops.split_bf16(W, ncols=H, col_offset=n0, want_lo=lo)
+                    ops.gemm_nt(dp_hi, dp_lo, w_hi, w_lo, BT, F, dp_hi.shape[1], out=tmp, ldc=F, passes=passes)
+                    ops.mask_mul_acc(dx2, tmp, masks[dg], T, accumulate=dg > 0)
+            dx = dx2.reshape(B, T, F)
+        return dx, dW, dU, db, None, None
+
+
+def blstm(x, W, U, b, masks=None, passes=None):
+    """Functional form.  W (F,8H) = [fwd kernel | bwd kernel]; U (2,H,4H); b (8H);
+    masks None or (8, B, F): input-dropout masks for (dir, gate) = (0,i),(0,f),(0,c),(0,o),(1,i).."""
+    return _BlstmFn.apply(x, W, U, b, masks, GEMM_PASSES if passes is None else passes)
+
+
+class _DirView:
+    """`.forward_layer` / `.backward_layer` handle carrying the `.trainable` flag (multimodal.py:47-48)."""
+
+    def __init__(self, owner):
+        self._owner = owner
+        self._trainable = True
+
+    @property
+    def trainable(self):
+        return self._trainable
+
+    @trainable.setter
+    def trainable(self, v):
+        self._trainable = bool(v)
+        self._owner._sync_trainable()
+
+
+class BidirectionalLSTM(nn.Module):
+    def __init__(self, input_dim, units, dropout=0.0, max_norm=3.0, seed=47, name=None):
+        super().__init__()
+        self.input_dim, self.units, self.dropout, self.max_norm = input_dim, units, float(dropout), max_norm
+        self.name = name
+        F, H = input_dim, units
+        rng = np.random.default_rng(seed)
+        W = rng.uniform(-0.05, 0.05, size=(F, 8 * H)).astype(np.float32)
+        U = np.stack([_orthogonal(rng, H, 4 * H) for _ in range(2)]).astype(np.float32)
+        b = np.zeros(8 * H, dtype=np.float32)
+        b[H:2 * H] = 1.0          # unit_forget_bias, forward layer
+        b[5 * H:6 * H] = 1.0      # backward layer
+        self.kernel = nn.Parameter(torch.from_numpy(W))
+        self.recurrent_kernel = nn.Parameter(torch.from_numpy(U))
+        self.bias = nn.Parameter(torch.from_numpy(b))
+        self.trainable = True
+        self.forward_layer = _DirView(self)
+        self.backward_layer = _DirView(self)
+        self.training_phase = True  # K.set_learning_phase(1): dropout active (speech:40)
+
+    def _sync_trainable(self):
+        # the reference freezes by flipping forward_layer/backward_layer.trainable (multimodal.py:43-48)
+        on = self.forward_layer.trainable and self.backward_layer.trainable
+        for p in (self.kernel, self.recurrent_kernel, self.bias):
+            p.requires_grad_(on)
+
+    def get_weights(self):
+        H = self.units
+        W, U, b = self.kernel.detach().cpu().numpy(), self.recurrent_kernel.detach().cpu().numpy(), \
+            self.bias.detach().cpu().numpy()
+        return [W[:, :4 * H].copy(), U[0].copy(), b[:4 * H].copy(), W[:, 4 * H:].copy(), U[1].copy(),
+                b[4 * H:].copy()]
+
+    def set_weights(self, weights):
+        fk, fr, fb, bk, br, bb = [np.asarray(w, dtype=np.float32) for w in weights]
+        dev = self.kernel.device
+        with torch.no_grad():
+            self.kernel.copy_(torch.from_numpy(np.concatenate([fk, bk], axis=1)).to(dev))
+            self.recurrent_kernel.copy_(torch.from_numpy(np.stack([fr, br])).to(dev))
+            self.bias.copy_(torch.from_numpy(np.concatenate([fb, bb])).to(dev))
+
+    def make_masks(self, B, seed, offset):
+        """4 masks per direction, shape (B,F), scaled 1/(1-p), constant over time."""
+        if self.dropout <= 0.0:
+            return None
+        return ops.dropout_mask((8, B, self.input_dim), self.dropout, seed, offset, self.kernel.device)
+
+    def forward(self, x, masks=None):
+        return blstm(x, self.kernel, self.recurrent_kernel, self.bias, masks)
+
+
+class _DenseSoftmaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, Wd, bd, drop_mask):
+        shp = x.shape
+        x2 = x.contiguous().reshape(-1, shp[-1])
+        m2 = None if drop_mask is None else drop_mask.contiguous().reshape(-1, shp[-1])
+        logits, probs = ops.dense_softmax_fwd(x2, Wd, bd, m2)
+        ctx.save_for_backward(x2, Wd, m2, probs)
+        ctx.shp = shp
+        C = Wd.shape[1]
+        return probs.reshape(shp[:-1] + (C,)), logits.reshape(shp[:-1] + (C,))
+
+    @staticmethod
+    def backward(ctx, g_probs, g_logits):
+        x2, Wd, m2, probs = ctx.saved_tensors
+        C = Wd.shape[1]
+        g = torch.zeros_like(probs)
+        if g_probs is not None:
+            gp = g_probs.reshape(-1, C)
+            g = g + probs * (gp - (probs * gp).sum(dim=1, keepdim=True))  # softmax backward (unfused path)
+        if g_logits is not None:
+            g = g + g_logits.reshape(-1, C)
+        dW, db, dx = ops.dense_bwd(x2, Wd, g.contiguous(), m2, want_dx=ctx.needs_input_grad[0])
+        return (None if dx is None else dx.reshape(ctx.shp)), dW, db, None
+
+
+class DenseSoftmax(nn.Module):
+    """Dense(nb_classes, kernel_initializer=RandomUniform(+-0.05, seed=47)) + Activation('softmax')."""
+
+    def __init__(self, input_dim, nb_classes, seed=47):
+        super().__init__()
+        rng = np.random.default_rng(seed + 1)
+        self.kernel = nn.Parameter(torch.from_numpy(rng.uniform(-0.05, 0.05, size=(input_dim, nb_classes)).astype(np.float32)))
+        self.bias = nn.Parameter(torch.zeros(nb_classes))
+
+    def get_weights(self):
+        return [self.kernel.detach().cpu().numpy().copy(), self.bias.detach().cpu().numpy().copy()]
+
+    def set_weights(self, weights):
+        with torch.no_grad():
+            self.kernel.copy_(torch.as_tensor(np.asarray(weights[0], dtype=np.float32)).to(self.kernel.device))
+            self.bias.copy_(torch.as_tensor(np.asarray(weights[1], dtype=np.float32)).to(self.bias.device))
+
+    def forward(self, x, drop_mask=None):
+        """Returns (softmax probabilities, logits)."""
+        return _DenseSoftmaxFn.apply(x, self.kernel, self.bias, drop_mask)
+
+
+def _orthogonal(rng, rows, cols):
+    a = rng.standard_normal((max(rows, cols), min(rows, cols)))
+    q, r = np.linalg.qr(a)
+    q = q * np.sign(np.diag(r))
+    q = q if rows >= cols else q.T
+    return q[:rows, :cols]

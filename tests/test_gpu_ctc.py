@@ -1,0 +1,122 @@
+"""Parity of the CUDA CTC kernel (through the C ABI) against the oracle.
+Tolerances (BASELINE.json north_star): loss 1e-4 relative, gradients 1e-3 (fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import random_probs, random_labels
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-4
+GRAD_TOL = 1e-3
+
+
+def _run(mgr, dev, p, labels, il, ll, logits=None):
+    if logits is None:
+        y = torch.tensor(p, device=dev, requires_grad=True)
+        loss = mgr.ctc_lambda_func([y, torch.tensor(labels), torch.tensor(il), torch.tensor(ll)])
+    else:
+        y = torch.tensor(logits, device=dev, requires_grad=True)
+        loss = mgr.softmax_ctc(y, torch.tensor(labels), torch.tensor(il), torch.tensor(ll))
+    loss.mean().backward()
+    return loss.detach().cpu().numpy().astype(np.float64), y.grad.detach().cpu().numpy().astype(np.float64)
+
+
+@pytest.mark.parametrize("B,T,C,Lmax", [(4, 12, 5, 3), (8, 50, 22, 10), (3, 33, 44, 40), (5, 130, 22, 35),
+                                        (2, 70, 6, 33), (2, 300, 22, 150)])
+def test_loss_and_grad_match_oracle(cuda, B, T, C, Lmax):
+    import mgr_b200 as mgr
+    from oracle import ctc_ref
+    rng = np.random.default_rng(B * 1000 + T)
+    p, _ = random_probs(rng, B, T, C)
+    il = rng.integers((T - 2) // 2 + 1, T - 1, size=(B, 1))
+    il[0, 0] = T - 2
+    labels, ll = random_labels(rng, B, Lmax, C, T_avail=il[:, 0])
+    loss, grad = _run(mgr, cuda, p, labels, il, ll)
+    ref_loss, ref_g = ctc_ref.ctc_lambda_func((p, labels, il, ll), want_grad=True)
+    ref_g = ref_g / B
+    assert np.abs(loss - ref_loss).max() <= LOSS_RTOL * np.abs(ref_loss).max()
+    # gradient wrt probabilities: compare relative to the row scale (1/(p+eps) can be large)
+    scale = np.abs(ref_g).max(axis=2, keepdims=True) + 1e-12
+    assert (np.abs(grad - ref_g) / scale).max() <= GRAD_TOL
+    assert np.all(grad[:, :2] == 0)
+    for b in range(B):
+        assert np.all(grad[b, 2 + il[b, 0]:] == 0)
+
+
+@pytest.mark.parametrize("B,T,C,Lmax", [(4, 40, 22, 8), (2, 200, 22, 35), (3, 64, 44, 20)])
+def test_fused_logit_mode(cuda, B, T, C, Lmax):
+    import mgr_b200 as mgr
+    from oracle import ctc_ref
+    rng = np.random.default_rng(7 + T)
+    _, a = random_probs(rng, B, T, C)
+    il = np.full((B, 1), T - 2)
+    labels, ll = random_labels(rng, B, Lmax, C, T_avail=il[:, 0])
+    loss, grad = _run(mgr, cuda, None, labels, il, ll, logits=a)
+    ref_loss, ref_g = ctc_ref.softmax_ctc_grad_logits(a, labels, il, ll)
+    assert np.abs(loss - ref_loss).max() <= LOSS_RTOL * np.abs(ref_loss).max()
+    assert np.abs(grad - ref_g).max() <= GRAD_TOL * np.abs(ref_g).max()
+
+
+def test_edge_cases(cuda):
+    import mgr_b200 as mgr
+    from oracle import ctc_ref
+    C = 5
+    rng = np.random.default_rng(3)
+    p, _ = random_probs(rng, 5, 9, C)
+    # blank-only label -> empty target; T'=1; repeated labels just feasible; B=1 batch (Keras squeeze bug n/a)
+    labels = np.array([[4, -1, -1], [1, -1, -1], [2, 2, -1], [0, 1, 0], [3, 4, -1]], dtype=np.float32)
+    ll = np.array([[1], [1], [2], [3], [2]])
+    il = np.array([[7], [1], [3], [5], [7]])
+    loss, grad = _run(mgr, cuda, p, labels, il, ll)
+    ref_loss, ref_g = ctc_ref.ctc_lambda_func((p, labels, il, ll), want_grad=True)
+    assert np.abs(loss - ref_loss).max() <= LOSS_RTOL * np.abs(ref_loss).max()
+    scale = np.abs(ref_g).max(axis=2, keepdims=True) + 1e-12
+    assert (np.abs(grad - ref_g / 5) / scale).max() <= GRAD_TOL
+    l1, _ = _run(mgr, cuda, p[:1], labels[:1], il[:1], ll[:1])
+    assert abs(l1[0, 0] - ref_loss[0, 0]) <= LOSS_RTOL * abs(ref_loss[0, 0])
+
+
+def test_no_valid_path_gives_inf_like_tf(cuda):
+    import mgr_b200 as mgr
+    p = torch.full((1, 4, 4), 0.25, device=cuda)
+    loss = mgr.ctc_lambda_func([p, torch.tensor([[1.0, 1.0]]), torch.tensor([[2]]), torch.tensor([[2]])])
+    assert torch.isinf(loss).all()
+
+
+@pytest.mark.parametrize("labels,ll,il", [([[0.0]], [[0]], [[6]]), ([[3.0, 1.0]], [[2]], [[6]]),
+                                           ([[0.0] * 7], [[7]], [[6]]), ([[0.0]], [[1]], [[9]])])
+def test_tf_error_behaviour(cuda, labels, ll, il):
+    import mgr_b200 as mgr
+    p = torch.full((1, 8, 4), 0.25, device=cuda)
+    with pytest.raises(mgr.InvalidArgumentError):
+        mgr.ctc_lambda_func([p, torch.tensor(labels), torch.tensor(il), torch.tensor(ll)])
+
+
+def test_full_size_properties(cuda):
+    """BASELINE config 4 size (B=1024, T=1000, L<=40, C=22): size-independent properties --
+    grad wrt logits sums to zero over classes, frames 0,1 are zero, and a spot-checked subset of
+    sequences matches the oracle."""
+    import mgr_b200 as mgr
+    from oracle import ctc_ref
+    B, T, C, Lmax = 1024, 1002, 22, 40
+    g = torch.Generator(device="cpu").manual_seed(3001)
+    a = (torch.randn(B, T, C, generator=g) * 2).to(cuda)
+    rng = np.random.default_rng(3002)
+    labels, ll = random_labels(rng, B, Lmax, C)
+    il = np.full((B, 1), T - 2)
+    y = a.clone().requires_grad_(True)
+    loss = mgr.softmax_ctc(y, torch.tensor(labels), torch.tensor(il), torch.tensor(ll))
+    loss.sum().backward()
+    gsum = y.grad.sum(dim=2).abs().max().item()
+    assert gsum < 1e-4
+    assert torch.all(y.grad[:, :2] == 0)
+    assert torch.isfinite(loss).all()
+    idx = [0, 511, 1023]
+    ref_loss, ref_g = ctc_ref.softmax_ctc_grad_logits(a[idx].cpu().numpy(), labels[idx], il[idx], ll[idx],
+                                                      upstream=np.ones(3))
+    got = loss[idx].detach().cpu().numpy()
+    assert np.abs(got - ref_loss).max() <= LOSS_RTOL * np.abs(ref_loss).max()
+    gg = y.grad[idx].cpu().numpy()
+    assert np.abs(gg - ref_g).max() <= GRAD_TOL * np.abs(ref_g).max()
