@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- fusion BLSTM-CTC training throughput (BASELINE.json config 3) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W     # CPU restatement of the reference path
+
+A "step" is one full training step of multimodal_fusion/multimodal.py on synthetic data:
+frozen speech+skeletal towers (dropout/noise active, learning phase 1) -> concat -> BLSTM(100) ->
+Dropout -> Dense(22) -> fused softmax+CTC loss/grad -> BPTT through the fusion BLSTM -> one flat
+NCCL all-reduce of the 1 365 222 trainable gradients -> Adam(clipvalue)+maxnorm.  Global batch 256,
+T=1000, sharded over the ranks (strong scaling, as BASELINE.json states the config).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GLOBAL_BATCH = 256
+T_FRAMES = 1000
+NB_CLASSES = 22
+LMAX = 35
+METRIC = "fusion BLSTM-CTC train seq/s"
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synth_batch(rows_lo, rows_hi, T):
+    """Rows [lo,hi) of the GLOBAL synthetic batch (seeds 2001/2002/2003: SURVEY.md 8d config 3)."""
+    import torch
+    ga = torch.Generator().manual_seed(2001)
+    gs = torch.Generator().manual_seed(2002)
+    xa = torch.randn(GLOBAL_BATCH, T, 39, generator=ga)[rows_lo:rows_hi].contiguous()
+    xs = torch.randn(GLOBAL_BATCH, T, 20, generator=gs)[rows_lo:rows_hi].contiguous()
+    rng = np.random.default_rng(2003)
+    labels = -np.ones((GLOBAL_BATCH, LMAX), dtype=np.float32)
+    ll = np.zeros((GLOBAL_BATCH, 1), dtype=np.int64)
+    for b in range(GLOBAL_BATCH):
+        L = int(rng.integers(1, LMAX + 1))
+        labels[b, :L] = rng.integers(0, NB_CLASSES - 1, size=L)
+        ll[b, 0] = L
+    il = np.full((GLOBAL_BATCH, 1), T - 2, dtype=np.int64)
+    return xa, xs, torch.from_numpy(labels[rows_lo:rows_hi]), torch.from_numpy(il[rows_lo:rows_hi]), \
+        torch.from_numpy(ll[rows_lo:rows_hi])
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_step_time(n_seq, T, steps=1, warmup=0):
+    """The restated reference path (oracle/lstm_ref.py, torch CPU fp32, all host threads):
+    fusion forward (towers + fusion BLSTM + Dense + softmax), ctc loss, backward through the
+    fusion BLSTM + Dense.  Returns (seconds per step, threads)."""
+    import torch
+    from oracle import lstm_ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    rng = np.random.default_rng(47)
+    t32 = lambda ws: [torch.tensor(w) for w in ws]
+    sp1, sp2 = t32(lstm_ref.init_blstm_weights(rng, 39, 500)), t32(lstm_ref.init_blstm_weights(rng, 1000, 500))
+    sk1, sk2 = t32(lstm_ref.init_blstm_weights(rng, 20, 300)), t32(lstm_ref.init_blstm_weights(rng, 600, 300))
+    fu = [w.requires_grad_(True) for w in t32(lstm_ref.init_blstm_weights(rng, 1600, 100))]
+    fd = [w.requires_grad_(True) for w in t32(lstm_ref.init_dense_weights(rng, 200, NB_CLASSES))]
+    xa, xs, labels, il, ll = synth_batch(0, n_seq, T)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        noise = torch.randn_like(xa) * 0.5
+        masks = {"fu_f": (torch.rand(4, n_seq, 1600) > 0.5).float() * 2, "fu_b": (torch.rand(4, n_seq, 1600) > 0.5).float() * 2}
+        p, a, _ = lstm_ref.fusion_forward(xa, xs, sp1, sp2, sk1, sk2, fu, fd, noise_a=noise, masks=masks,
+                                          drop_mask=(torch.rand(n_seq, T, 200) > 0.5).float() * 2)
+        loss = lstm_ref.torch_ctc_lambda(p, labels, il, ll).mean()
+        loss.backward()
+        for w in fu + fd:
+            w.grad = None
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return float(np.mean(times)), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_seq = args.ref_batch
+    sec, threads = cpu_reference_step_time(n_seq, T_FRAMES, steps=args.steps, warmup=min(args.warmup, 1))
+    v = n_seq / sec
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "seq/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "fusion BLSTM-CTC training step (multimodal.py), T=1000, C=22; CPU sample of "
+                                   "%d sequences per step" % n_seq, "global_batch": GLOBAL_BATCH, "seq_len": T_FRAMES},
+            "cpu_baseline": {"value": v, "unit": "seq/s", "cores": threads, "kind": "port",
+                             "sample": "%d sequences x T=%d per step, %d steps, torch-CPU fp32 restatement "
+                                       "(oracle/lstm_ref.py)" % (n_seq, T_FRAMES, args.steps)},
+            "e2e": {"value": v, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+def ctc_microbench(dev, peak_gbs):
+    """BASELINE config 4 point: B=1024, T=1000 (+2 dropped), L=40, C=22; CUDA events, L2-exceeding
+    working set (lattice 360 MB + probs/grad 180 MB)."""
+    import torch
+    from mgr_b200 import ops
+    B, T, C, L = 1024, 1002, 22, 40
+    g = torch.Generator().manual_seed(3001)
+    probs = torch.softmax(torch.randn(B, T, C, generator=g) * 2, -1).to(dev)
+    rng = np.random.default_rng(3002)
+    labels = torch.tensor(rng.integers(0, C - 1, size=(B, L)), dtype=torch.int32, device=dev)
+    ll = torch.full((B,), L, dtype=torch.int32, device=dev)
+    il = torch.full((B,), T - 2, dtype=torch.int32, device=dev)
+    for _ in range(3):
+        ops.ctc_loss_grad(probs, labels, ll, il, False)
+    torch.cuda.synchronize()
+    n = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        ops.ctc_loss_grad(probs, labels, ll, il, False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    frames = B * (T - 2)
+    bytes_per_frame = 8 * C + 8 * (2 * L + 1) + (4 * L + 16) / (T - 2)
+    achieved = frames * bytes_per_frame / (ms * 1e-3) / 1e9
+    return {"workload": "ctc loss+grad B=1024 T=1000 L=40 C=22 (config 4)", "ms": ms,
+            "frames_per_s": frames / (ms * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                         "frac": achieved / peak_gbs, "traffic": None,
+                         "algorithmic_bytes_per_frame": bytes_per_frame}}
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import mgr_b200 as mgr
+    from mgr_b200 import parallel, _lib
+
+    rank, world, local = parallel.init_from_env()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    hbm_peak, tc_peak, peak_kind = read_peaks()
+    lo, hi = parallel.shard_rows(GLOBAL_BATCH, rank, world)
+    B = hi - lo
+    T = args.seq_len
+
+    model = mgr.FusionNet().to(dev)
+    opt = mgr.fusion_optimizer(model)
+    bucket = parallel.FlatGradBucket(model.trainable_parameters())
+    xa_h, xs_h, lab_h, il_h, ll_h = [t.pin_memory() for t in synth_batch(lo, hi, T)]
+    xa_d, xs_d = xa_h.to(dev), xs_h.to(dev)
+    h2d_bytes = sum(t.numel() * t.element_size() for t in (xa_h, xs_h, lab_h, il_h, ll_h))
+
+    step_no = [0]
+
+    def train_step(xa, xs, lab, il, ll):
+        reg = model.sample_regularisers(B, T, seed=1234 + rank, step=step_no[0], device=dev)
+        loss, grads = model.loss_and_grads(xa, xs, lab, il, ll, reg, global_batch=GLOBAL_BATCH)
+        bucket.pack(grads)
+        views = bucket.all_reduce()
+        opt.step(views)
+        step_no[0] += 1
+        return loss
+
+    lab_d, il_d, ll_d = lab_h.to(dev), il_h.to(dev), ll_h.to(dev)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident arm
+    for _ in range(max(args.warmup, 3)):
+        train_step(xa_d, xs_d, lab_d, il_d, ll_d)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count
+    _lib.kernel_timing_begin(["gr_lstm_recurrence_fwd_f32", "gr_lstm_recurrence_bwd_f32", "gr_gemm_bf16x3_f32",
+                              "gr_ctc_loss_grad_f32", "gr_split_bf16_f32"])
+    total_ms = timed(lambda: train_step(xa_d, xs_d, lab_d, il_d, ll_d), args.steps)
+    ktimes = _lib.kernel_timing_end()
+    launches = _lib.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = GLOBAL_BATCH / (ms_per_step * 1e-3)
+
+    # ---- end-to-end arm: pinned host inputs -> H2D every step, loss read back every step
+    losses = []
+
+    def e2e_step():
+        xa = xa_h.to(dev, non_blocking=True)
+        xs = xs_h.to(dev, non_blocking=True)
+        lab, il, ll = lab_h.to(dev, non_blocking=True), il_h.to(dev, non_blocking=True), ll_h.to(dev, non_blocking=True)
+        loss = train_step(xa, xs, lab, il, ll)
+        losses.append(loss.cpu())
+
+    e2e_step()
+    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    e2e_value = GLOBAL_BATCH / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (share of the step measured with CUDA events)
+    per_kernel = {k: {"ms_per_step": sum(v) / args.steps, "launches_per_step": len(v) / args.steps,
+                      "avg_ms": sum(v) / max(1, len(v))} for k, v in ktimes.items()}
+    dom = max(per_kernel.items(), key=lambda kv: kv[1]["ms_per_step"])[0] if per_kernel else None
+    roofline = None
+    if dom == "gr_lstm_recurrence_fwd_f32" or dom == "gr_lstm_recurrence_bwd_f32":
+        # algorithmic bytes of the recurrence per launch, both directions:
+        # read 4H pre-activations + write h (+ 4H gates + c when kept for BPTT) per (b, t, unit)
+        calls = _lib.kernel_timing_shapes.get(dom, [])
+        tot_bytes = sum(c for c in calls) / max(1, len(calls))
+        avg_ms = per_kernel[dom]["avg_ms"]
+        ach = tot_bytes / (avg_ms * 1e-3) / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                    "avg_launch_ms": avg_ms, "share_of_step": per_kernel[dom]["ms_per_step"] / ms_per_step}
+    elif dom == "gr_gemm_bf16x3_f32":
+        calls = _lib.kernel_timing_shapes.get(dom, [])
+        flops = sum(calls) / max(1, len(calls))
+        avg_ms = per_kernel[dom]["avg_ms"]
+        ach = flops / (avg_ms * 1e-3) / 1e12
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s",
+                    "frac": ach / tc_peak, "traffic": None, "peak_kind": peak_kind, "avg_launch_ms": avg_ms,
+                    "share_of_step": per_kernel[dom]["ms_per_step"] / ms_per_step,
+                    "note": "algorithmic flops 2MNK (bf16x3 executes 3x that on the tensor pipe)"}
+    ctc = ctc_microbench(dev, hbm_peak) if not args.skip_ctc else None
+    cpu = None
+    if not args.skip_cpu:
+        sec, threads = cpu_reference_step_time(args.ref_batch, T, steps=1, warmup=0)
+        cpu = {"value": args.ref_batch / sec, "unit": "seq/s", "cores": threads, "kind": "port",
+               "sample": "%d sequences x T=%d, 1 step, torch-CPU fp32 restatement (oracle/lstm_ref.py), %.1f s"
+                         % (args.ref_batch, T, sec)}
+    line = {"metric": METRIC, "value": value, "unit": "seq/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "fusion BLSTM-CTC training step (multimodal.py topology: speech 39->2xBLSTM500, "
+                                   "skeletal 20->2xBLSTM300 frozen, fusion BLSTM100 + Dense22 + CTC trained), "
+                                   "regularisers on (Philox)", "global_batch": GLOBAL_BATCH, "per_gpu_batch": B,
+                       "seq_len": T, "classes": NB_CLASSES, "parallelism": "dp%d" % world,
+                       "projection_arithmetic": "bf16x3 split on tcgen05 (fp32-faithful)",
+                       "l2": "per-step activation working set (>10 GB) exceeds the 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e_value, "unit": "seq/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": B * 4},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": per_kernel,
+            "ctc": ctc, "cpu_baseline": cpu, "loss_mean": float(torch.cat(losses).mean())}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--seq-len", type=int, default=T_FRAMES)
+    ap.add_argument("--ref-batch", type=int, default=4, help="sequences per CPU-baseline step (bounded sample)")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-ctc", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

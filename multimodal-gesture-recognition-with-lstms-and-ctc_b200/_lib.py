@@ -97,6 +97,8 @@ def ptr(t):
     """Device pointer of a torch tensor (None -> NULL)."""
     if t is None:
         return None
+    if not t.is_contiguous():
+        raise GrError("non-contiguous tensor passed to the C ABI (shape %s, strides %s)" % (tuple(t.shape), t.stride()))
     return c_void_p(t.data_ptr())
 
 

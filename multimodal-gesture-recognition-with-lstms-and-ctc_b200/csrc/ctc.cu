@@ -147,7 +147,10 @@ __global__ void __launch_bounds__(64) ctc_loss_grad_kernel(CtcParams p) {
   const float up_scale = p.upstream ? p.upstream[b] : 1.0f;
   const float eps = p.eps;
 
-  float logp2 = 0.f;
+  // Renormalisation: states are kept relative to a running offset `off` (double), re-centred on
+  // the warp maximum once per chunk, so fp32 never has to resolve 1e-7 at magnitude 1e3..1e4.
+  double off = 0.0;
+  double logp2 = 0.0;
   bool novalid = false;
   float lpb_last = kNeg, lpl_last[K];
 #pragma unroll
@@ -205,6 +208,22 @@ __global__ void __launch_bounds__(64) ctc_loss_grad_kernel(CtcParams p) {
         Zrow = Z;
       }
       __syncwarp();
+      // ---- re-centre the states on their maximum (once per chunk; uniform across the warp)
+      if (ic > 0) {
+        float mx = kNeg;
+#pragma unroll
+        for (int j = 0; j < K; ++j) mx = fmaxf(mx, fmaxf(sb[j], sl[j]));
+        mx = warp_max(mx);
+        if (mx > -1.0e29f) {
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            sb[j] = fmaxf(sb[j] - mx, kNeg);
+            sl[j] = fmaxf(sl[j] - mx, kNeg);
+          }
+          off += (double)mx;
+        }
+      }
+      const float off_hi = (float)off, off_lo = (float)(off - (double)off_hi);
       // ---- the serial part
       for (int i = ic; i < ie; ++i) {
         const int r = dir == 0 ? i - ic : ie - 1 - i;
@@ -241,6 +260,7 @@ __global__ void __launch_bounds__(64) ctc_loss_grad_kernel(CtcParams p) {
             if (vb[j]) dst[posb[j]] = sb[j];
             if (vl[j]) dst[posl[j]] = sl[j];
           }
+          if (lane == 0) { dst[RS - 2] = off_hi; dst[RS - 1] = off_lo; }
           if (i == ie - 1) {
             lpb_last = lpb;
 #pragma unroll
@@ -248,10 +268,12 @@ __global__ void __launch_bounds__(64) ctc_loss_grad_kernel(CtcParams p) {
           }
         } else {
           float* erow = Es + r * RSp;
+          // (my offset + the other direction's offset at this row - log p): small, formed in double
+          const float cst = (float)(off + (double)erow[RS - 2] + (double)erow[RS - 1] - logp2);
 #pragma unroll
           for (int j = 0; j < K; ++j) {
-            if (vb[j]) erow[posb[j]] = novalid ? 0.f : ex2_approx(sb[j] + erow[posb[j]] - lpb - logp2);
-            if (vl[j]) erow[posl[j]] = novalid ? 0.f : ex2_approx(sl[j] + erow[posl[j]] - lpl[j] - logp2);
+            if (vb[j]) erow[posb[j]] = novalid ? 0.f : ex2_approx((sb[j] + erow[posb[j]] - lpb) + cst);
+            if (vl[j]) erow[posl[j]] = novalid ? 0.f : ex2_approx((sl[j] + erow[posl[j]] - lpl[j]) + cst);
           }
         }
       }
@@ -319,13 +341,17 @@ __global__ void __launch_bounds__(64) ctc_loss_grad_kernel(CtcParams p) {
         for (int j = 0; j < 2 * K; ++j) s += ex2_approx(v[j] - m);
         s = warp_sum(s);
         const float lp2 = m + lg2_approx(s);
-        if (lane == 0) bcast[0] = lp2;
+        if (lane == 0) {
+          const bool nv = !(m > -1.0e29f) || !(lp2 > -1.0e29f);
+          double* bd = reinterpret_cast<double*>(bcast);
+          bd[0] = nv ? -1.0e300 : off + (double)orow[RS - 2] + (double)orow[RS - 1] + (double)lp2;
+        }
       }
       __syncthreads();
-      logp2 = bcast[0];
-      novalid = !(logp2 > -1.0e29f);
+      logp2 = reinterpret_cast<const double*>(bcast)[0];
+      novalid = !(logp2 > -1.0e299);
       if (threadIdx.x == 0) {
-        p.loss[b] = novalid ? __int_as_float(0x7f800000) : -logp2 * kLn2;
+        p.loss[b] = novalid ? __int_as_float(0x7f800000) : (float)(-logp2 * 0.6931471805599453);
         if (p.status) p.status[b] = novalid ? GR_CTC_NO_VALID_PATH : GR_CTC_OK;
       }
     }
@@ -336,7 +362,7 @@ static size_t ctc_smem_bytes(int C, int Lmax, int RS, int TC) {
   size_t fl = ((Lmax + 3) & ~3) + 4 + 2 * (size_t)(2 * TC * ctc_cp(C) + TC * ctc_rsp(RS));
   return fl * sizeof(float);
 }
-static int ctc_row_stride(int Lmax) { return (2 * Lmax + 1 + 7) & ~7; }
+static int ctc_row_stride(int Lmax) { return (2 * Lmax + 3 + 7) & ~7; }  // +2: per-row offset (hi, lo)
 
 template <int K>
 static int launch_ctc(const CtcParams& p, cudaStream_t stream) {

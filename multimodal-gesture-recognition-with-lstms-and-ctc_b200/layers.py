@@ -43,7 +43,9 @@ class _BlstmFn(torch.autograd.Function):
     def forward(ctx, x, W, U, b, masks, passes):
         B, T, F = x.shape
         H = U.shape[1]
-        x = x.contiguous()
+        # raw pointers cross the C ABI: every operand must be dense row-major
+        x, W, U, b = x.contiguous(), W.contiguous(), U.contiguous(), b.contiguous()
+        masks = None if masks is None else masks.contiguous()
         x2 = x.reshape(B * T, F)
         need_grad = any(ctx.needs_input_grad[:4])
         gates = _project(x2, W, b, masks, B, T, H, passes)
@@ -140,9 +142,9 @@ class BidirectionalLSTM(nn.Module):
         b = np.zeros(8 * H, dtype=np.float32)
         b[H:2 * H] = 1.0          # unit_forget_bias, forward layer
         b[5 * H:6 * H] = 1.0      # backward layer
-        self.kernel = nn.Parameter(torch.from_numpy(W))
-        self.recurrent_kernel = nn.Parameter(torch.from_numpy(U))
-        self.bias = nn.Parameter(torch.from_numpy(b))
+        self.kernel = nn.Parameter(torch.from_numpy(np.ascontiguousarray(W)))
+        self.recurrent_kernel = nn.Parameter(torch.from_numpy(np.ascontiguousarray(U)))
+        self.bias = nn.Parameter(torch.from_numpy(np.ascontiguousarray(b)))
         self.trainable = True
         self.forward_layer = _DirView(self)
         self.backward_layer = _DirView(self)
@@ -185,6 +187,7 @@ class _DenseSoftmaxFn(torch.autograd.Function):
         shp = x.shape
         x2 = x.contiguous().reshape(-1, shp[-1])
         m2 = None if drop_mask is None else drop_mask.contiguous().reshape(-1, shp[-1])
+        Wd, bd = Wd.contiguous(), bd.contiguous()
         logits, probs = ops.dense_softmax_fwd(x2, Wd, bd, m2)
         ctx.save_for_backward(x2, Wd, m2, probs)
         ctx.shp = shp
