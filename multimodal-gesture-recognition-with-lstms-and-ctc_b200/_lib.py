@@ -83,12 +83,50 @@ def exported_symbols():
     return sorted(_SIGNATURES)
 
 
+# ---- optional per-kernel CUDA-event timing (bench.py: roofline of the dominant kernel) --------
+_timing = None            # name -> [(start_event, end_event), ...]
+_pending_work = None
+kernel_timing_shapes = {}  # name -> [algorithmic bytes or flops of each timed launch]
+
+
+def kernel_timing_begin(names):
+    global _timing
+    _timing = {n: [] for n in names}
+    kernel_timing_shapes.clear()
+
+
+def kernel_timing_end():
+    """Synchronise and return name -> [ms per launch]."""
+    global _timing
+    import torch
+    torch.cuda.synchronize()
+    out = {n: [a.elapsed_time(b) for a, b in evs] for n, evs in (_timing or {}).items() if evs}
+    _timing = None
+    return out
+
+
+def note_work(amount):
+    """Algorithmic bytes/flops of the NEXT call (recorded only while timing is on)."""
+    global _pending_work
+    _pending_work = amount
+
+
 def call(name, *args):
-    global launch_count
+    global launch_count, _pending_work
     lib = load()
+    timed = _timing is not None and name in _timing
+    if timed:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(lib, name)(*args)
     if rc != GR_OK:
         raise GrError("%s failed with code %d: %s" % (name, rc, lib.gr_last_error().decode()))
+    if timed:
+        e1.record()
+        _timing[name].append((e0, e1))
+        kernel_timing_shapes.setdefault(name, []).append(_pending_work or 0)
+    _pending_work = None
     launch_count += 1
     return rc
 

@@ -10,6 +10,7 @@
 // needed for the cell update).  Per step the CTAs of one direction exchange h_t through a
 // transposed (H, B) buffer in L2 and a monotonic counter barrier.  `gates` is used in place:
 // pre-activations P in, post-activation gates out (forward), dP out (backward).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace gr {
@@ -274,6 +275,18 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
   }
 }
 
+// tensor-core forward path (lstm_tc.cu)
+bool lstm_tc_supported(int B, int H);
+size_t lstm_tc_workspace_bytes(int B, int H);
+int lstm_fwd_tc_launch(float* gates, const float* U, int B, int T, int H, float* y, float* cell, void* workspace,
+                       cudaStream_t s);
+
+static bool use_tc_path(int B, int H) {
+  const char* e = getenv("GR_LSTM_IMPL");
+  if (e && strcmp(e, "generic") == 0) return false;
+  return lstm_tc_supported(B, H);
+}
+
 static void lstm_config(int B, int H, int* HS, int* UG, int* Bp) {
   const int per_dir = max(1, num_sms() / 2);
   int hs = (H + per_dir - 1) / per_dir;
@@ -289,7 +302,9 @@ extern "C" int gr_lstm_workspace_bytes(int B, int H, size_t* bytes_out) {
   if (B <= 0 || H <= 0 || !bytes_out) return gr::set_error(GR_EINVAL, "lstm_workspace_bytes: bad argument");
   const size_t Bp = (B + 3) & ~3;
   // counters (256 B) + dG^T exchange (2*2*4H*Bp) [the h^T exchange aliases it] + carried state (2*B*H)
-  *bytes_out = 256 + sizeof(float) * ((size_t)16 * H * Bp + (size_t)2 * B * H) + 256;
+  size_t generic = 256 + sizeof(float) * ((size_t)16 * H * Bp + (size_t)2 * B * H) + 256;
+  size_t tc = gr::lstm_tc_supported(B, H) ? gr::lstm_tc_workspace_bytes(B, H) : 0;
+  *bytes_out = generic > tc ? generic : tc;
   return GR_OK;
 }
 
@@ -302,6 +317,8 @@ extern "C" int gr_lstm_recurrence_fwd_f32(float* gates, const float* U, int B, i
   size_t need = 0;
   gr_lstm_workspace_bytes(B, H, &need);
   if (workspace_bytes < need) return set_error(GR_EWORKSPACE, "lstm_fwd: workspace too small");
+  if (use_tc_path(B, H))
+    return lstm_fwd_tc_launch(gates, U, B, T, H, y, cell, workspace, static_cast<cudaStream_t>(stream));
   LstmFwdParams p;
   lstm_config(B, H, &p.HS, &p.UG, &p.Bp);
   if (2 * p.UG > num_sms()) return set_error(GR_EUNSUPPORTED, "lstm_fwd: H too large for the resident-U kernel");

@@ -122,6 +122,7 @@ def gemm_nt(a_hi, a_lo, b_hi, b_lo, M, N, K, out=None, ldc=None, bias=None, accu
         out = torch.empty((M, N), dtype=torch.float32, device=a_hi.device)
         ldc = N
     cptr = ctypes.c_void_p(out.data_ptr() + 4 * out_col_offset)
+    _lib.note_work(2.0 * M * N * K)
     call("gr_gemm_bf16x3_f32", ptr(a_hi), ptr(a_lo), ptr(b_hi), ptr(b_lo), ptr(bias), cptr, int(ldc), int(M),
          int(N), int(K), a_hi.stride(0), b_hi.stride(0), int(passes), int(bool(accumulate)), stream_ptr())
     return out
@@ -151,6 +152,8 @@ def lstm_recurrence_fwd(gates, U, B, T, H, keep_cell=True):
     y = torch.empty((B, T, 2 * H), dtype=torch.float32, device=gates.device)
     cell = torch.empty((B, T, 2 * H), dtype=torch.float32, device=gates.device) if keep_cell else None
     ws = lstm_workspace(B, H, gates.device)
+    # algorithmic bytes: read 4H pre-activations, write h (+ 4H gates + c when kept)
+    _lib.note_work(float(B) * T * 2 * H * (40 if keep_cell else 20))
     call("gr_lstm_recurrence_fwd_f32", ptr(gates), ptr(U), B, T, H, ptr(y), ptr(cell), ptr(ws), ws.numel(),
          stream_ptr())
     return y, cell
@@ -159,6 +162,7 @@ def lstm_recurrence_fwd(gates, U, B, T, H, keep_cell=True):
 def lstm_recurrence_bwd(gates, cell, dy, U, B, T, H):
     require_cuda(gates, cell, dy, U)
     ws = lstm_workspace(B, H, gates.device)
+    _lib.note_work(float(B) * T * 2 * H * 44)  # read gates 16 + c,c_prev 8 + dy 4, write dP 16
     call("gr_lstm_recurrence_bwd_f32", ptr(gates), ptr(cell), ptr(_f32c(dy)), ptr(U), B, T, H, ptr(ws),
          ws.numel(), stream_ptr())
     return gates  # now dP
