@@ -281,9 +281,20 @@ size_t lstm_tc_workspace_bytes(int B, int H);
 int lstm_fwd_tc_launch(float* gates, const float* U, int B, int T, int H, float* y, float* cell, void* workspace,
                        cudaStream_t s);
 
+// register-resident-U path for narrow layers (lstm_small.cu)
+bool lstm_small_supported(int H);
+int lstm_small_run(bool bwd, float* gates, const float* U, int B, int T, int H, float* y, float* cell,
+                   const float* dy, cudaStream_t s);
+
+// GR_LSTM_IMPL = generic | tc | small forces one implementation (debugging / cross-checks)
+static bool use_small_path(int H) {
+  const char* e = getenv("GR_LSTM_IMPL");
+  if (e && strcmp(e, "small") != 0) return false;
+  return lstm_small_supported(H);
+}
 static bool use_tc_path(int B, int H) {
   const char* e = getenv("GR_LSTM_IMPL");
-  if (e && strcmp(e, "generic") == 0) return false;
+  if (e && strcmp(e, "tc") != 0) return false;
   return lstm_tc_supported(B, H);
 }
 
@@ -317,6 +328,8 @@ extern "C" int gr_lstm_recurrence_fwd_f32(float* gates, const float* U, int B, i
   size_t need = 0;
   gr_lstm_workspace_bytes(B, H, &need);
   if (workspace_bytes < need) return set_error(GR_EWORKSPACE, "lstm_fwd: workspace too small");
+  if (use_small_path(H))
+    return lstm_small_run(false, gates, U, B, T, H, y, cell, nullptr, static_cast<cudaStream_t>(stream));
   if (use_tc_path(B, H))
     return lstm_fwd_tc_launch(gates, U, B, T, H, y, cell, workspace, static_cast<cudaStream_t>(stream));
   LstmFwdParams p;
@@ -347,6 +360,8 @@ extern "C" int gr_lstm_recurrence_bwd_f32(float* gates, const float* cell, const
   size_t need = 0;
   gr_lstm_workspace_bytes(B, H, &need);
   if (workspace_bytes < need) return set_error(GR_EWORKSPACE, "lstm_bwd: workspace too small");
+  if (use_small_path(H))
+    return lstm_small_run(true, gates, U, B, T, H, nullptr, const_cast<float*>(cell), dy, static_cast<cudaStream_t>(stream));
   LstmBwdParams p;
   lstm_config(B, H, &p.HS, &p.UG, &p.Bp);
   if (2 * p.UG > num_sms()) return set_error(GR_EUNSUPPORTED, "lstm_bwd: H too large for the resident-U kernel");

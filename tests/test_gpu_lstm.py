@@ -114,3 +114,32 @@ def test_long_sequence_stability(cuda):
     y = layer(torch.tensor(x, device=cuda)).detach().cpu().numpy()
     ref = lstm_ref.bidirectional_lstm(torch.tensor(x, dtype=torch.float64), [torch.tensor(a, dtype=torch.float64) for a in w6]).numpy()
     assert np.abs(y - ref).max() < 1e-3
+
+
+@pytest.mark.parametrize("impl,B,T,F,H", [("generic", 5, 9, 16, 36), ("tc", 5, 9, 16, 36), ("tc", 130, 6, 24, 100),
+                                          ("small", 9, 11, 16, 100), ("generic", 9, 7, 16, 100)])
+def test_every_recurrence_implementation(cuda, monkeypatch, impl, B, T, F, H):
+    """The three recurrence kernels (generic fp32 / tcgen05 / register-resident) agree with the
+    oracle on the same inputs (GR_LSTM_IMPL forces one)."""
+    import mgr_b200 as mgr
+    monkeypatch.setenv("GR_LSTM_IMPL", impl)
+    for attempt in range(20):
+        rng = np.random.default_rng(H + 31 * attempt)
+        x = rng.standard_normal((B, T, F)).astype(np.float32)
+        W = rng.uniform(-0.3, 0.3, size=(F, 8 * H)).astype(np.float32)
+        U = (rng.standard_normal((2, H, 4 * H)) / np.sqrt(H)).astype(np.float32)
+        b = (rng.standard_normal(8 * H) * 0.2).astype(np.float32)
+        dy = rng.standard_normal((B, T, 2 * H)).astype(np.float32)
+        if _gate_margin(x, W, U, b, None) > 2e-4:
+            break
+    xt, Wt, Ut, bt = [torch.tensor(a, device=cuda, requires_grad=True) for a in (x, W, U, b)]
+    y = mgr.blstm(xt, Wt, Ut, bt)
+    y.backward(torch.tensor(dy, device=cuda))
+    torch.cuda.synchronize()
+    ry, rdx, rdW, rdU, rdb = _ref(x, W, U, b, None, dy)
+    tol = lambda r: 1e-3 * max(1.0, np.abs(r).max())
+    assert np.abs(y.detach().cpu().numpy() - ry).max() <= 2e-4
+    assert np.abs(xt.grad.cpu().numpy() - rdx).max() <= tol(rdx)
+    assert np.abs(Wt.grad.cpu().numpy() - rdW).max() <= tol(rdW)
+    assert np.abs(Ut.grad.cpu().numpy() - rdU).max() <= tol(rdU)
+    assert np.abs(bt.grad.cpu().numpy() - rdb).max() <= tol(rdb)
