@@ -249,7 +249,7 @@ def run_gpu(args):
         return float(ms.item())
 
     # ---- device-resident arm
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, args.min_warmup)):
         train_step(xa_d, xs_d, lab_d, il_d, ll_d)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -274,6 +274,8 @@ def run_gpu(args):
         loss = train_step(xa, xs, lab, il, ll)
         losses.append(loss.cpu())
 
+    if args.skip_e2e:
+        return
     e2e_step()
     e2e_ms = timed(e2e_step, args.steps) / args.steps
     e2e_value = GLOBAL_BATCH / (e2e_ms * 1e-3)
@@ -315,7 +317,7 @@ def run_gpu(args):
                "sample": "%d sequences x T=%d, 1 step, torch-CPU fp32 restatement (oracle/lstm_ref.py), %.1f s"
                          % (args.ref_batch, T, sec)}
     line = {"metric": METRIC, "value": value, "unit": "seq/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "warmup": max(args.warmup, args.min_warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "fusion BLSTM-CTC training step (multimodal.py topology: speech 39->2xBLSTM500, "
                                    "skeletal 20->2xBLSTM300 frozen, fusion BLSTM100 + Dense22 + CTC trained), "
@@ -342,6 +344,8 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=4, help="sequences per CPU-baseline step (bounded sample)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-ctc", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
+    ap.add_argument("--min-warmup", type=int, default=3, help="profiling runs only (ncu launch lists)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

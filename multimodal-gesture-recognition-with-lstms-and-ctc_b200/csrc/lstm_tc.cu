@@ -18,7 +18,8 @@
 
 namespace gr {
 
-static constexpr int kTcThreads = 192;
+static constexpr int kTcThreads = 320;  // TMA warp, MMA warp, 8 epilogue warps
+static constexpr int kEU = 8;           // units per epilogue thread
 static constexpr int kUnits = 16;       // hidden units per CTA
 static constexpr int kNcols = 64;       // 4 gates x 16 units
 static constexpr int kStages = 2;
@@ -34,6 +35,12 @@ struct LstmTcParams {
 };
 
 __device__ __forceinline__ float hsig(float v) { return fminf(fmaxf(0.2f * v + 0.5f, 0.f), 1.f); }
+// tanh(x) = 1 - 2/(1 + e^{2x}) on MUFU ex2 + IEEE division: absolute error ~1e-7 (the libm tanhf
+// costs ~30 instructions and sat on the per-step critical path of every recurrence step)
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float e = ex2_approx(x * 2.8853900817779268f);  // e^{2x}
+  return 1.0f - __fdividef(2.0f, 1.0f + e);
+}
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmHh, const __grid_constant__ CUtensorMap tmHl,
@@ -141,78 +148,101 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmHh, const __grid_consta
       }
     }
   } else {
-    // ---- epilogue: thread <-> batch row
+    // ---- epilogue: 8 warps; thread <-> (batch row, half of the 16 units).  Warp w may only touch
+    // TMEM lanes 32*(w%4)..+31, so warps w and w+4 share a row group and split the units.
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int b = bt * 128 + q * 32 + lane;
     const bool bok = b < p.B;
     const size_t G8 = (size_t)8 * H, Y2 = (size_t)2 * H;
-    int nu = H - j0;                       // valid units in this group
-    if (nu > kUnits) nu = kUnits;
-    float c_state[kUnits];
+    const int ju = j0 + half * kEU;        // first unit of this thread
+    int nu = H - ju;                        // valid units for this thread (multiple of 4)
+    if (nu > kEU) nu = kEU;
+    if (nu < 0) nu = 0;
+    float c_state[kEU];
 #pragma unroll
-    for (int u = 0; u < kUnits; ++u) c_state[u] = 0.f;
+    for (int u = 0; u < kEU; ++u) c_state[u] = 0.f;
     for (int s = 0; s < T; ++s) {
       const int t = dir == 0 ? s : T - 1 - s;
-      float pre[4][kUnits];
-      float* grow = p.gates + ((size_t)b * T + t) * G8 + (size_t)dir * 4 * H + j0;
-      if (bok) {
+      float pre[4][kEU];
+      float* grow = p.gates + ((size_t)b * T + t) * G8 + (size_t)dir * 4 * H + ju;
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
+      for (int g = 0; g < 4; ++g)
 #pragma unroll
-          for (int u4 = 0; u4 < kUnits; u4 += 4) {
-            if (u4 < nu) {
-              const float4 v = *reinterpret_cast<const float4*>(grow + (size_t)g * H + u4);
-              pre[g][u4] = v.x; pre[g][u4 + 1] = v.y; pre[g][u4 + 2] = v.z; pre[g][u4 + 3] = v.w;
-            } else {
-              pre[g][u4] = pre[g][u4 + 1] = pre[g][u4 + 2] = pre[g][u4 + 3] = 0.f;
-            }
+        for (int u4 = 0; u4 < kEU; u4 += 4) {
+          if (bok && u4 < nu) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(grow + (size_t)g * H + u4));
+            pre[g][u4] = v.x; pre[g][u4 + 1] = v.y; pre[g][u4 + 2] = v.z; pre[g][u4 + 3] = v.w;
+          } else {
+            pre[g][u4] = pre[g][u4 + 1] = pre[g][u4 + 2] = pre[g][u4 + 3] = 0.f;
           }
-      } else {
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-#pragma unroll
-          for (int u = 0; u < kUnits; ++u) pre[g][u] = 0.f;
-      }
+        }
       if (s > 0) {
         mbar_wait(tmem_full, (uint32_t)((s - 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t v[4][kEU];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          uint32_t v[16];
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * kUnits);
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * kUnits + half * kEU);
           asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+              "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+              : "=r"(v[g][0]), "=r"(v[g][1]), "=r"(v[g][2]), "=r"(v[g][3]), "=r"(v[g][4]), "=r"(v[g][5]),
+                "=r"(v[g][6]), "=r"(v[g][7])
               : "r"(taddr)
               : "memory");
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int u = 0; u < kUnits; ++u) pre[g][u] += __uint_as_float(v[u]);
         }
-      }
-      float hv[kUnits];
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int u = 0; u < kUnits; ++u) {
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int u = 0; u < kEU; ++u) pre[g][u] += __uint_as_float(v[g][u]);
+      }
+      float hv[kEU];
+#pragma unroll
+      for (int u = 0; u < kEU; ++u) {
         const float gi = hsig(pre[0][u]);
         const float gf = hsig(pre[1][u]);
-        const float gg = tanhf(pre[2][u]);
+        const float gg = tanh_fast(pre[2][u]);
         const float go = hsig(pre[3][u]);
         const float c = gf * c_state[u] + gi * gg;
         c_state[u] = c;
-        hv[u] = go * tanhf(c);
+        hv[u] = go * tanh_fast(c);
         pre[0][u] = gi; pre[1][u] = gf; pre[2][u] = gg; pre[3][u] = go;
       }
       if (bok) {
-        float* yrow = p.y + ((size_t)b * T + t) * Y2 + (size_t)dir * H + j0;
+        if (s + 1 < T) {
+          // publish h_t first (it is on the critical path of every CTA of this group)
+          uint32_t hi_w[kEU / 2], lo_w[kEU / 2];
 #pragma unroll
-        for (int u4 = 0; u4 < kUnits; u4 += 4)
-          if (u4 < nu) *reinterpret_cast<float4*>(yrow + u4) = make_float4(hv[u4], hv[u4 + 1], hv[u4 + 2], hv[u4 + 3]);
+          for (int u = 0; u < kEU; u += 2) {
+            const float a0 = (u < nu) ? hv[u] : 0.f, a1 = (u + 1 < nu) ? hv[u + 1] : 0.f;
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(a0 - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(a1 - __bfloat162float(h1));
+            hi_w[u / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lo_w[u / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          }
+          const size_t off = ((size_t)(dir * 2 + (s & 1)) * p.Bpad + b) * p.Kp64 + ju;
+          *reinterpret_cast<uint4*>(p.hb_hi + off) = make_uint4(hi_w[0], hi_w[1], hi_w[2], hi_w[3]);
+          *reinterpret_cast<uint4*>(p.hb_lo + off) = make_uint4(lo_w[0], lo_w[1], lo_w[2], lo_w[3]);
+        }
+      }
+      if (s + 1 < T) {
+        __threadfence();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 64) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+      }
+      if (bok) {
+        // off the critical path: the layer output and (training) the saved gates / cell state
+        float* yrow = p.y + ((size_t)b * T + t) * Y2 + (size_t)dir * H + ju;
+#pragma unroll
+        for (int u4 = 0; u4 < kEU; u4 += 4)
+          if (u4 < nu) __stcs(reinterpret_cast<float4*>(yrow + u4), make_float4(hv[u4], hv[u4 + 1], hv[u4 + 2], hv[u4 + 3]));
         if (p.save) {
-          float* crow = p.cell + ((size_t)b * T + t) * Y2 + (size_t)dir * H + j0;
+          float* crow = p.cell + ((size_t)b * T + t) * Y2 + (size_t)dir * H + ju;
 #pragma unroll
-          for (int u4 = 0; u4 < kUnits; u4 += 4)
+          for (int u4 = 0; u4 < kEU; u4 += 4)
             if (u4 < nu) {
               *reinterpret_cast<float4*>(crow + u4) = make_float4(c_state[u4], c_state[u4 + 1], c_state[u4 + 2], c_state[u4 + 3]);
 #pragma unroll
@@ -221,33 +251,6 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmHh, const __grid_consta
                     make_float4(pre[g][u4], pre[g][u4 + 1], pre[g][u4 + 2], pre[g][u4 + 3]);
             }
         }
-        if (s + 1 < T) {
-          // publish h_t as bf16 hi/lo rows of the exchange buffer (units >= H stay zero)
-          uint32_t hi_w[kUnits / 2], lo_w[kUnits / 2];
-#pragma unroll
-          for (int u = 0; u < kUnits; u += 2) {
-            const float a0 = (u < nu) ? hv[u] : 0.f, a1 = (u + 1 < nu) ? hv[u + 1] : 0.f;
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(a0 - __bfloat162float(h0));
-            const __nv_bfloat16 l1 = __float2bfloat16_rn(a1 - __bfloat162float(h1));
-            hi_w[u / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lo_w[u / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-          }
-          const size_t off = ((size_t)(dir * 2 + (s & 1)) * p.Bpad + b) * p.Kp64 + j0;
-          uint4* dh = reinterpret_cast<uint4*>(p.hb_hi + off);
-          uint4* dl = reinterpret_cast<uint4*>(p.hb_lo + off);
-          dh[0] = make_uint4(hi_w[0], hi_w[1], hi_w[2], hi_w[3]);
-          dh[1] = make_uint4(hi_w[4], hi_w[5], hi_w[6], hi_w[7]);
-          dl[0] = make_uint4(lo_w[0], lo_w[1], lo_w[2], lo_w[3]);
-          dl[1] = make_uint4(lo_w[4], lo_w[5], lo_w[6], lo_w[7]);
-        }
-      }
-      if (s + 1 < T) {
-        asm volatile("fence.proxy.async;" ::: "memory");
-        __threadfence();
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
       }
     }
   }

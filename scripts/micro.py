@@ -1,0 +1,29 @@
+"""Micro-workloads for ncu captures: `python scripts/micro.py ctc|lstm_tc|gemm`."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from mgr_b200 import ops, layers
+dev = torch.device("cuda:0")
+what = sys.argv[1]
+if what == "ctc":
+    B, T, C, L = 1024, 1002, 22, 40
+    g = torch.Generator().manual_seed(3001)
+    probs = torch.softmax(torch.randn(B, T, C, generator=g) * 2, -1).to(dev)
+    rng = np.random.default_rng(3002)
+    labels = torch.tensor(rng.integers(0, C - 1, size=(B, L)), dtype=torch.int32, device=dev)
+    ll = torch.full((B,), L, dtype=torch.int32, device=dev); il = torch.full((B,), T - 2, dtype=torch.int32, device=dev)
+    for _ in range(3):
+        ops.ctc_loss_grad(probs, labels, ll, il, False)
+elif what == "lstm_tc":
+    B, T, H = 256, 200, 500
+    gates = torch.randn(B * T, 8 * H, device=dev) * 0.5
+    U = torch.randn(2, H, 4 * H, device=dev) / H ** 0.5
+    for _ in range(2):
+        ops.lstm_recurrence_fwd(gates.clone(), U, B, T, H, keep_cell=False)
+elif what == "gemm":
+    M, N, K = 65536, 4000, 1000
+    x = torch.randn(M, K, device=dev); W = torch.randn(K, N, device=dev) * 0.05
+    a = ops.split_bf16(x); w = ops.split_bf16(W, transpose=True)
+    for _ in range(2):
+        ops.gemm_nt(a[0], a[1], w[0], w[1], M, N, K)
+torch.cuda.synchronize()

@@ -72,3 +72,35 @@ def test_full_size_config5(cuda):
     for j in (0, 100, 511):
         assert got[j] == decode_ref.decode_ids_literal(s[j], 0.5)
     assert all(all(a != b for a, b in zip(g[:-1], g[1:])) for g in got)  # collapsed: no adjacent repeats
+
+
+@pytest.mark.parametrize("W,top,merge", [(100, 1, True), (100, 3, False), (4, 2, True), (1, 1, True)])
+def test_beam_search_bit_exact_vs_c_oracle(cuda, W, top, merge):
+    import mgr_b200 as mgr
+    from oracle import beam_c
+    rng = np.random.default_rng(4001 + W)
+    N, T, C = 6, 160, 22
+    s = peaky_probs(rng, N, T, C, sharp=3.0)
+    sl = rng.integers(T // 2, T + 1, size=N)
+    sl[0] = T
+    dec, logp = mgr.ctc_decode(s, sl, greedy=False, beam_width=W, top_paths=top, merge_repeated=merge)
+    for j in range(N):
+        ref = beam_c.beam_search(s[j], int(sl[j]), W, top, merge)
+        for k in range(top):
+            got = [int(v) for v in dec[k][j].cpu().numpy() if v >= 0]
+            assert got == ref[k][0], (j, k)
+            assert np.float32(logp[j, k].item()) == np.float32(ref[k][1])  # bit-exact log-probability
+
+
+def test_beam_search_unpeaky_and_other_class_counts(cuda):
+    import mgr_b200 as mgr
+    from oracle import beam_c
+    rng = np.random.default_rng(77)
+    for (N, T, C, W) in [(3, 40, 5, 16), (2, 64, 44, 100), (2, 30, 3, 100)]:
+        s = rng.random((N, T, C)).astype(np.float32) ** 2
+        s /= s.sum(2, keepdims=True)
+        dec, logp = mgr.ctc_decode(s, np.full(N, T), greedy=False, beam_width=W, top_paths=1)
+        for j in range(N):
+            ref = beam_c.beam_search(s[j], T, W, 1, True)
+            assert [int(v) for v in dec[0][j].cpu().numpy() if v >= 0] == ref[0][0]
+            assert np.float32(logp[j, 0].item()) == np.float32(ref[0][1])
