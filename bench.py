@@ -256,7 +256,7 @@ def run_gpu(args):
         sampler.start()
     launches0 = _lib.launch_count
     _lib.kernel_timing_begin(["gr_lstm_recurrence_fwd_f32", "gr_lstm_recurrence_bwd_f32", "gr_gemm_bf16x3_f32",
-                              "gr_ctc_loss_grad_f32", "gr_split_bf16_f32"])
+                              "gr_ctc_loss_grad_f32", "gr_split_bf16_f32", "gr_gemm_a32_f32"])
     total_ms = timed(lambda: train_step(xa_d, xs_d, lab_d, il_d, ll_d), args.steps)
     ktimes = _lib.kernel_timing_end()
     launches = _lib.launch_count - launches0
@@ -300,7 +300,7 @@ def run_gpu(args):
         roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": ach / hbm_peak, "traffic": None, "peak_kind": peak_kind,
                     "avg_launch_ms": avg_ms, "share_of_step": per_kernel[dom]["ms_per_step"] / ms_per_step}
-    elif dom == "gr_gemm_bf16x3_f32":
+    elif dom in ("gr_gemm_bf16x3_f32", "gr_gemm_a32_f32"):
         calls = _lib.kernel_timing_shapes.get(dom, [])
         flops = sum(calls) / max(1, len(calls))
         avg_ms = per_kernel[dom]["avg_ms"]

@@ -139,6 +139,18 @@ int gr_lstm_recurrence_bwd_f32(float* gates /* in: i,f,g,o ; out: dP */, const f
 int gr_gemm_bf16x3_f32(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
                        const float* bias, float* C, int ldc, int M, int N, int K, int lda, int ldb,
                        int passes, int accumulate, void* stream);
+/* Projection GEMM with the fp32 prologue FUSED (no bf16 copy of the activations in HBM):
+ *   for v in [0, nvar):  C[:, v*Nv:(v+1)*Nv] (+)= op(A, mask_v) * B[v*Nv:(v+1)*Nv, :]^T + bias
+ * A fp32: transA == 0 -> (M, K) row-major, mask_v[(m / rows_per_seq) * K + k];
+ *         transA != 0 -> (K, M) row-major, element (m,k) = A[(k + row_shift) * lda + m] when row
+ *         k + row_shift lies in the same sequence of rows_per_seq rows (else 0),
+ *         mask_v[(k / rows_per_seq) * M + m].   mask: (nvar, n_sequences, K or M) or NULL --
+ *         the per-gate LSTM input-dropout masks (speech_lstm_ctc_words.py:61,73).
+ * B: pre-split bf16 hi/lo, (nvar*Nv, ldb) K-major, zero padded to ldb (multiple of 8) columns. */
+int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shift, const float* mask,
+                    int rows_per_seq, int nvar, const void* b_hi, const void* b_lo, int ldb,
+                    const float* bias, float* C, int ldc, int M, int Nv, int K, int accumulate,
+                    void* stream);
 /* plain fp32 CUDA-core GEMM with the same contract on unsplit operands (cross-check only). */
 int gr_gemm_simt_f32(const float* A, const float* B, const float* bias, float* C, int M, int N,
                      int K, int lda, int ldb, int ldc, int accumulate, void* stream);

@@ -44,6 +44,8 @@ _SIGNATURES = {
     "gr_lstm_recurrence_bwd_f32": ([_P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P], c_int),
     "gr_gemm_bf16x3_f32": ([_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
                            c_int),
+    "gr_gemm_a32_f32": ([_P, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int,
+                         c_int, _P], c_int),
     "gr_gemm_simt_f32": ([_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P], c_int),
     "gr_split_bf16_f32": ([_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, _P], c_int),
     "gr_mask_mul_acc_f32": ([_P, _P, _P, c_int, c_int, c_int, c_int, _P], c_int),

@@ -1,0 +1,489 @@
+// Projection GEMM with a FUSED fp32 prologue, tcgen05 + TMA, sm_100a.
+//
+//   for v in [0, nvar):   C[:, v*Nv : (v+1)*Nv]  (+)=  op(A, mask_v) * B[v*Nv : (v+1)*Nv, :]^T  + bias
+//
+// A is the fp32 activation tensor itself (never materialised as bf16 in HBM): the four
+// "epilogue" warps spend the main loop as A-PRODUCERS -- they load the fp32 tile with coalesced
+// 128-bit loads, apply the per-sequence LSTM input-dropout mask of gate/direction variant v
+// (/root/reference/audio_network/speech_lstm_ctc_words.py:61,73 `dropout=`; Keras applies one
+// mask per gate to x before each gate's matmul), split every value into bf16 hi + lo and store
+// both in the SWIZZLE_128B K-major layout that tcgen05.mma reads.  transA != 0 reads A as
+// (K, M) -- the X^T / H_prev^T operands of the BPTT weight-gradient contractions -- with an
+// optional time shift inside each sequence (h_{t-1} / h_{t+1} pairing for dU).
+// B (weights, or dP^T) arrives pre-split through TMA.  Arithmetic: bf16x3, fp32 accumulate.
+#include <stdlib.h>
+#include "tc_common.cuh"
+
+namespace gr {
+
+static constexpr int kA32Threads = 320;  // TMA warp, MMA warp, 8 producer/epilogue warps
+
+struct A32Params {
+  const float* A;
+  const float* mask;     // (nvar, nseq, Kdim) or null;  Kdim = K (!transA) or M (transA)
+  const float* bias;     // (nvar*Nv) or null
+  float* C;
+  long long mask_var_stride;
+  int lda, ldc, M, Nv, K, BN, nvar, ntile, rows_per_seq, row_shift, transA, aligned4;
+  int kb_total, kb_per_split, stages, use_atomic, tmem_cols;
+};
+
+__device__ __forceinline__ void split2(float v, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi = __bfloat16_as_ushort(h);
+  lo = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+}
+
+// pack two floats into bf16x2 (hi) and the bf16x2 of their residuals (lo); element a in the low half
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float fa = __uint_as_float(hi << 16), fb = __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - fa, b - fb);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// MODE 0: generic producer (any alignment, any sequence length)
+// MODE 1: fast row-major A   (lda, K multiples of 4; a 128-row tile spans <= 2 sequences)
+// MODE 2: fast transposed A  (a 64-row k-block spans <= 2 sequences)
+template <int MODE>
+__global__ void __launch_bounds__(kA32Threads, 1)
+gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, A32Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int BN = p.BN;
+  const uint32_t a_bytes = 128 * kBK * 2;
+  const uint32_t b_bytes = (uint32_t)BN * kBK * 2;
+  const uint32_t stage_bytes = 2 * (a_bytes + b_bytes);
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* fullB = fullA + p.stages;
+  uint64_t* empty = fullB + p.stages;
+  uint64_t* tmem_full = empty + p.stages;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int var = blockIdx.x / p.ntile, nt = blockIdx.x % p.ntile;
+  const int m0 = blockIdx.y * 128, n0 = nt * BN;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
+  const int nkb = kb_end - kb_begin;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBh)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBl)) : "memory");
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&fullA[s], 256); mbar_init(&fullB[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (i / p.stages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* st = smem + (size_t)s * stage_bytes + 2 * a_bytes;
+        mbar_expect_tx(&fullB[s], 2 * b_bytes);
+        const int k0 = (kb_begin + i) * kBK;
+        tma_load_2d(st, &tmBh, &fullB[s], k0, var * p.Nv + n0);
+        tma_load_2d(st + b_bytes, &tmBl, &fullB[s], k0, var * p.Nv + n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (i / p.stages) & 1;
+        mbar_wait(&fullB[s], ph);
+        mbar_wait(&fullA[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint64_t dAh = make_sw128_desc(sa);
+        const uint64_t dAl = make_sw128_desc(sa + a_bytes);
+        const uint64_t dBh = make_sw128_desc(sa + 2 * a_bytes);
+        const uint64_t dBl = make_sw128_desc(sa + 2 * a_bytes + b_bytes);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          const uint64_t adv = (uint64_t)(k * 2);
+          umma_bf16(tmem_base, dAh + adv, dBh + adv, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(tmem_base, dAh + adv, dBl + adv, idesc, 1u);
+          umma_bf16(tmem_base, dAl + adv, dBh + adv, idesc, 1u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // =============== A producers (main loop), then epilogue: 8 warps, 256 threads ===============
+    const int t = threadIdx.x - 64;  // 0..255
+    const float* mv = p.mask ? p.mask + (long long)var * p.mask_var_stride : nullptr;
+    if constexpr (MODE == 1) {
+      // ---------------- fast row-major producer ----------------
+      const int kq = t & 15, rbase = t >> 4;             // float4 column, first row; rows rbase + 16 j
+      const int T_ = p.rows_per_seq;
+      const int seqA = m0 / T_;
+      const int rbound = (seqA + 1) * T_ - m0;           // tile rows >= rbound belong to sequence seqA+1
+      const int nseq = (p.M + T_ - 1) / T_;
+      const float* ap[8];
+      bool rok[8], selB[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = rbase + 16 * j;
+        rok[j] = m0 + r < p.M;
+        selB[j] = r >= rbound;
+        ap[j] = p.A + (size_t)(rok[j] ? m0 + r : 0) * p.lda + kq * 4;
+      }
+      const float* mpA = mv ? mv + (size_t)seqA * p.K + kq * 4 : nullptr;
+      const float* mpB = mv ? mv + (size_t)min(seqA + 1, nseq - 1) * p.K + kq * 4 : nullptr;
+      const uint32_t off0 = (uint32_t)rbase * 128u + ((((uint32_t)kq >> 1) ^ ((uint32_t)rbase & 7u)) << 4) + ((uint32_t)kq & 1u) * 8u;
+      const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 xa[8], xb[8], mAa = one4, mBa = one4, mAb = one4, mBb = one4;
+      auto ld = [&](int i, float4* x, float4& mA, float4& mB) {
+        const int koff = (kb_begin + i) * kBK;
+        const bool kv = koff + kq * 4 < p.K;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = (kv && rok[j]) ? __ldg(reinterpret_cast<const float4*>(ap[j] + koff)) : zero4;
+        if (mv) {
+          mA = kv ? __ldg(reinterpret_cast<const float4*>(mpA + koff)) : zero4;
+          mB = kv ? __ldg(reinterpret_cast<const float4*>(mpB + koff)) : zero4;
+        }
+      };
+      if (nkb > 0) ld(0, xa, mAa, mBa);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (i / p.stages) & 1;
+        uint8_t* Ah = smem + (size_t)s * stage_bytes + off0;
+        uint8_t* Al = Ah + a_bytes;
+        const bool odd = i & 1;
+        if (i + 1 < nkb) { if (odd) ld(i + 1, xa, mAa, mBa); else ld(i + 1, xb, mAb, mBb); }
+        mbar_wait(&empty[s], ph ^ 1);
+        const float4 mA = odd ? mAb : mAa, mB = odd ? mBb : mBa;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 x = odd ? xb[j] : xa[j];
+          const float4 mm = selB[j] ? mB : mA;
+          x.x *= mm.x; x.y *= mm.y; x.z *= mm.z; x.w *= mm.w;
+          uint32_t h01, l01, h23, l23;
+          split_pair(x.x, x.y, h01, l01);
+          split_pair(x.z, x.w, h23, l23);
+          *reinterpret_cast<uint2*>(Ah + j * 2048) = make_uint2(h01, h23);
+          *reinterpret_cast<uint2*>(Al + j * 2048) = make_uint2(l01, l23);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
+      }
+    } else if constexpr (MODE == 2) {
+      // ---------------- fast transposed producer ----------------
+      // warp w <-> k rows 8w..8w+7 of the k-block (one 16-byte chunk per output row);
+      // lane <-> m: rows lane + 32 g.  Loads are 128 B coalesced per k row; stores are STS.128.
+      const int w = t >> 5, ln = t & 31;
+      const int T_ = p.rows_per_seq;
+      const int nseq = (p.K + T_ - 1) / T_;
+      bool mok[4];
+      const float* ap[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) { const int m = m0 + ln + 32 * g; mok[g] = m < p.M; ap[g] = p.A + (mok[g] ? m : 0); }
+      const uint32_t off0 = (uint32_t)ln * 128u + (((uint32_t)w ^ ((uint32_t)ln & 7u)) << 4);
+      float xa[4][8], xb[4][8], ma[2][4], mb[2][4];
+      int selA_mask = 0, selB_mask = 0;   // bit kk set: row kk belongs to the second sequence of the block
+      auto ld = [&](int i, float (*x)[8], float (*mk)[4], int& sel) {
+        const int kbase = (kb_begin + i) * kBK + 8 * w;
+        const int seq0 = ((kb_begin + i) * kBK) / T_;
+        sel = 0;
+#pragma unroll
+        const int sqb = kbase / T_;
+        const int ttb = kbase - sqb * T_;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const int kg = kbase + kk;
+          const bool wrap = ttb + kk >= T_;            // T_ >= 64 > 8: at most one wrap inside the chunk
+          const int sq = sqb + (wrap ? 1 : 0);
+          const int tt = ttb + kk - (wrap ? T_ : 0) + p.row_shift;
+          const bool ok = kg < p.K && tt >= 0 && tt < T_;
+          if (sq != seq0) sel |= 1 << kk;
+          const size_t roff = (size_t)(ok ? kg + p.row_shift : 0) * p.lda;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) x[g][kk] = (ok && mok[g]) ? __ldg(ap[g] + roff) : 0.f;
+        }
+        if (mv) {
+#pragma unroll
+          for (int sI = 0; sI < 2; ++sI) {
+            const float* mp = mv + (size_t)min(seq0 + sI, nseq - 1) * p.M + m0 + ln;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) mk[sI][g] = mok[g] ? __ldg(mp + 32 * g) : 0.f;
+          }
+        }
+      };
+#pragma unroll
+      for (int sI = 0; sI < 2; ++sI)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) { ma[sI][g] = 1.f; mb[sI][g] = 1.f; }
+      if (nkb > 0) ld(0, xa, ma, selA_mask);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (i / p.stages) & 1;
+        uint8_t* Ah = smem + (size_t)s * stage_bytes + off0;
+        uint8_t* Al = Ah + a_bytes;
+        const bool odd = i & 1;
+        if (i + 1 < nkb) { if (odd) ld(i + 1, xa, ma, selA_mask); else ld(i + 1, xb, mb, selB_mask); }
+        mbar_wait(&empty[s], ph ^ 1);
+        const int sel = odd ? selB_mask : selA_mask;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float m_0 = odd ? mb[0][g] : ma[0][g], m_1 = odd ? mb[1][g] : ma[1][g];
+          uint32_t hh[4], ll[4];
+#pragma unroll
+          for (int kk = 0; kk < 8; kk += 2) {
+            const float a0 = (odd ? xb[g][kk] : xa[g][kk]) * (((sel >> kk) & 1) ? m_1 : m_0);
+            const float a1 = (odd ? xb[g][kk + 1] : xa[g][kk + 1]) * (((sel >> (kk + 1)) & 1) ? m_1 : m_0);
+            split_pair(a0, a1, hh[kk >> 1], ll[kk >> 1]);
+          }
+          *reinterpret_cast<uint4*>(Ah + g * 4096) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+          *reinterpret_cast<uint4*>(Al + g * 4096) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
+      }
+    } else {
+    constexpr int NV = 8;            // float4 per thread per k-block (128 x 64 floats / 256 threads / 4)
+    // per-thread static coordinates
+    int rr[NV], cc[NV];              // !transA: (row in tile, float4 index in row)   transA: (k row, float4 index over m)
+    int seq[NV], tin[NV];            // sequence id and position-in-sequence of the row that carries the mask
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int f = j * 256 + t;
+      if (!p.transA) { rr[j] = f >> 4; cc[j] = f & 15; const int m = m0 + rr[j]; seq[j] = m / p.rows_per_seq; tin[j] = 0; }
+      else { rr[j] = f >> 5; cc[j] = f & 31; const int kg = kb_begin * kBK + rr[j]; seq[j] = kg / p.rows_per_seq; tin[j] = kg - seq[j] * p.rows_per_seq; }
+    }
+    auto load_tile = [&](int i, float4* v) {
+      const int k0 = (kb_begin + i) * kBK;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!p.transA) {
+          const int m = m0 + rr[j], k = k0 + cc[j] * 4;
+          if (m < p.M && k < p.K) {
+            const float* src = p.A + (size_t)m * p.lda + k;
+            if (p.aligned4 && k + 3 < p.K) {
+              x = __ldg(reinterpret_cast<const float4*>(src));
+              if (mv) {
+                const float4 mm = __ldg(reinterpret_cast<const float4*>(mv + (size_t)seq[j] * p.K + k));
+                x.x *= mm.x; x.y *= mm.y; x.z *= mm.z; x.w *= mm.w;
+              }
+            } else {
+              const float* ms = mv ? mv + (size_t)seq[j] * p.K + k : nullptr;
+              x.x = src[0] * (ms ? ms[0] : 1.f);
+              if (k + 1 < p.K) x.y = src[1] * (ms ? ms[1] : 1.f);
+              if (k + 2 < p.K) x.z = src[2] * (ms ? ms[2] : 1.f);
+              if (k + 3 < p.K) x.w = src[3] * (ms ? ms[3] : 1.f);
+            }
+          }
+        } else {
+          const int kg = k0 + rr[j], m = m0 + cc[j] * 4;
+          const int tt = tin[j] + p.row_shift;
+          if (kg < p.K && m < p.M && tt >= 0 && tt < p.rows_per_seq) {
+            const float* src = p.A + (size_t)(kg + p.row_shift) * p.lda + m;
+            if (p.aligned4 && m + 3 < p.M) {
+              x = __ldg(reinterpret_cast<const float4*>(src));
+              if (mv) {
+                const float4 mm = __ldg(reinterpret_cast<const float4*>(mv + (size_t)seq[j] * p.M + m));
+                x.x *= mm.x; x.y *= mm.y; x.z *= mm.z; x.w *= mm.w;
+              }
+            } else {
+              const float* ms = mv ? mv + (size_t)seq[j] * p.M + m : nullptr;
+              x.x = src[0] * (ms ? ms[0] : 1.f);
+              if (m + 1 < p.M) x.y = src[1] * (ms ? ms[1] : 1.f);
+              if (m + 2 < p.M) x.z = src[2] * (ms ? ms[2] : 1.f);
+              if (m + 3 < p.M) x.w = src[3] * (ms ? ms[3] : 1.f);
+            }
+          }
+          // advance this row's (sequence, position) to the next k-block
+          tin[j] += kBK;
+          while (tin[j] >= p.rows_per_seq) { tin[j] -= p.rows_per_seq; ++seq[j]; }
+        }
+        v[j] = x;
+      }
+    };
+    float4 va[NV], vb[NV];
+    if (nkb > 0) load_tile(0, va);
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % p.stages;
+      const uint32_t ph = (i / p.stages) & 1;
+      uint8_t* Ah = smem + (size_t)s * stage_bytes;
+      uint8_t* Al = Ah + a_bytes;
+      float4* cur = (i & 1) ? vb : va;
+      float4* nxt = (i & 1) ? va : vb;
+      if (i + 1 < nkb) load_tile(i + 1, nxt);   // in flight while k-block i is converted
+      mbar_wait(&empty[s], ph ^ 1);
+      if (!p.transA) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const uint32_t r = (uint32_t)rr[j], kq = (uint32_t)cc[j];
+          uint32_t h0, l0, h1, l1, h2, l2, h3, l3;
+          split2(cur[j].x, h0, l0); split2(cur[j].y, h1, l1); split2(cur[j].z, h2, l2); split2(cur[j].w, h3, l3);
+          const uint32_t off = r * 128u + (((kq >> 1) ^ (r & 7u)) << 4) + (kq & 1u) * 8u;
+          *reinterpret_cast<uint2*>(Ah + off) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+          *reinterpret_cast<uint2*>(Al + off) = make_uint2(l0 | (l1 << 16), l2 | (l3 << 16));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const uint32_t kk = (uint32_t)rr[j], mq = (uint32_t)cc[j];
+          const float xs[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t r = mq * 4 + e;
+            uint32_t h, l;
+            split2(xs[e], h, l);
+            const uint32_t off = r * 128u + (((kk >> 3) ^ (r & 7u)) << 4) + (kk & 7u) * 2u;
+            *reinterpret_cast<uint16_t*>(Ah + off) = (uint16_t)h;
+            *reinterpret_cast<uint16_t*>(Al + off) = (uint16_t)l;
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
+    }
+    }
+    // ---- epilogue: warps w and w+4 share TMEM lanes 32*(w%4)..+31 and split the columns
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = m0 + q * 32 + lane;
+    const int cbase = var * p.Nv + n0;     // first output column of this tile
+    const bool add_bias = p.bias != nullptr && blockIdx.z == 0;
+    for (int c0 = half * 32; c0 < BN; c0 += 64) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < p.M && nkb > 0) {
+        float* crow = p.C + (size_t)row * p.ldc + cbase + c0;
+        const int ncol = min(32, min(BN - c0, p.Nv - (n0 + c0)));
+        const float* brow = p.bias ? p.bias + cbase + c0 : nullptr;
+        if (p.use_atomic) {
+          for (int c = 0; c < ncol; ++c) {
+            float x = __uint_as_float(v[c]);
+            if (add_bias) x += brow[c];
+            atomicAdd(crow + c, x);
+          }
+        } else if (ncol == 32 && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) &&
+                   (!add_bias || (reinterpret_cast<uintptr_t>(brow) & 15) == 0)) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            float4 o = make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+            if (add_bias) {
+              const float4 bb = *reinterpret_cast<const float4*>(brow + c);
+              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            }
+            *reinterpret_cast<float4*>(crow + c) = o;
+          }
+        } else {
+          for (int c = 0; c < ncol; ++c) {
+            float x = __uint_as_float(v[c]);
+            if (add_bias) x += brow[c];
+            crow[c] = x;
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+}  // namespace gr
+
+extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shift, const float* mask,
+                               int rows_per_seq, int nvar, const void* b_hi, const void* b_lo, int ldb,
+                               const float* bias, float* C, int ldc, int M, int Nv, int K, int accumulate,
+                               void* stream) {
+  using namespace gr;
+  if (!A || !b_hi || !b_lo || !C) return set_error(GR_EINVAL, "gemm_a32: null pointer");
+  if (M <= 0 || Nv <= 0 || K <= 0 || nvar <= 0 || rows_per_seq <= 0 || ldc < nvar * Nv)
+    return set_error(GR_EINVAL, "gemm_a32: bad shape");
+  if ((ldb % 8) || ldb < K) return set_error(GR_EINVAL, "gemm_a32: ldb must be a multiple of 8 and >= K");
+  if (!transA && lda < K) return set_error(GR_EINVAL, "gemm_a32: lda < K");
+  if (transA && lda < M) return set_error(GR_EINVAL, "gemm_a32: lda < M (transA)");
+  if (!transA && row_shift != 0) return set_error(GR_EUNSUPPORTED, "gemm_a32: row_shift needs transA");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  A32Params p;
+  p.A = A; p.mask = mask; p.bias = bias; p.C = C; p.lda = lda; p.ldc = ldc; p.M = M; p.Nv = Nv; p.K = K;
+  p.nvar = nvar; p.rows_per_seq = rows_per_seq; p.row_shift = row_shift; p.transA = transA ? 1 : 0;
+  const int seqs = ((transA ? K : M) + rows_per_seq - 1) / rows_per_seq;
+  p.mask_var_stride = (long long)seqs * (transA ? M : K);
+  const int inner = transA ? M : K;
+  p.aligned4 = ((lda % 4) == 0 && (inner % 4) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+                (!mask || (reinterpret_cast<uintptr_t>(mask) & 15) == 0)) ? 1 : 0;
+  // tile width: as few equal tiles as possible, each <= 256 and a multiple of 16
+  const int nt = (Nv + 255) / 256;
+  p.BN = (((Nv + nt - 1) / nt) + 15) / 16 * 16;
+  p.ntile = (Nv + p.BN - 1) / p.BN;
+  p.kb_total = (K + kBK - 1) / kBK;
+  const int mt = (M + 127) / 128;
+  const long long tiles = (long long)mt * p.ntile * nvar;
+  int splits = 1;
+  const int sms = num_sms();
+  if (tiles < sms && p.kb_total >= 8) {
+    splits = (int)min((long long)(2 * sms + tiles - 1) / tiles, (long long)p.kb_total / 4);
+    if (splits < 1) splits = 1;
+  }
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.use_atomic = (splits > 1 || accumulate) ? 1 : 0;
+  if (splits > 1 && !accumulate) GR_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)nvar * Nv * 4, M, s));
+  const size_t stage_bytes = 2 * ((size_t)128 * kBK * 2 + (size_t)p.BN * kBK * 2);
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > 4) stages = 4;
+  if (stages < 2) return set_error(GR_EUNSUPPORTED, "gemm_a32: tile does not fit shared memory");
+  p.stages = stages;
+  int tc = 32;
+  while (tc < p.BN) tc <<= 1;
+  p.tmem_cols = tc;
+  const size_t smem = 1024 + stages * stage_bytes + (3 * stages + 1) * 8 + 16;
+  CUtensorMap tBh, tBl;
+  int rc;
+  if ((rc = make_map(&tBh, b_hi, (uint64_t)nvar * Nv, ldb, ldb, p.BN)) != GR_OK) return rc;
+  if ((rc = make_map(&tBl, b_lo, (uint64_t)nvar * Nv, ldb, ldb, p.BN)) != GR_OK) return rc;
+  dim3 grid(p.ntile * nvar, mt, splits);
+  int mode = 0;
+  const char* force = getenv("GR_A32_MODE");
+  if (!transA && p.aligned4 && (!mask || rows_per_seq >= 128)) mode = 1;
+  if (transA && rows_per_seq >= 64) mode = 2;
+  if (force && force[0] == '0') mode = 0;
+  if (mode == 1) {
+    GR_CUDA(cudaFuncSetAttribute(gemm_a32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_a32_kernel<1><<<grid, kA32Threads, smem, s>>>(tBh, tBl, p);
+  } else if (mode == 2) {
+    GR_CUDA(cudaFuncSetAttribute(gemm_a32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_a32_kernel<2><<<grid, kA32Threads, smem, s>>>(tBh, tBl, p);
+  } else {
+    GR_CUDA(cudaFuncSetAttribute(gemm_a32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_a32_kernel<0><<<grid, kA32Threads, smem, s>>>(tBh, tBl, p);
+  }
+  GR_CHECK_LAUNCH("gemm_a32_kernel");
+  return GR_OK;
+}

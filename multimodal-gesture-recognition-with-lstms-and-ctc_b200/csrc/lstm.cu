@@ -278,6 +278,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(LstmBwdParams
 // tensor-core forward path (lstm_tc.cu)
 bool lstm_tc_supported(int B, int H);
 size_t lstm_tc_workspace_bytes(int B, int H);
+size_t lstm_tc_trace_offset(int B, int H);
 int lstm_fwd_tc_launch(float* gates, const float* U, int B, int T, int H, float* y, float* cell, void* workspace,
                        cudaStream_t s);
 
@@ -308,6 +309,8 @@ static void lstm_config(int B, int H, int* HS, int* UG, int* Bp) {
 }
 
 }  // namespace gr
+
+extern "C" size_t gr_debug_lstm_tc_trace_offset(int B, int H) { return gr::lstm_tc_trace_offset(B, H); }
 
 extern "C" int gr_lstm_workspace_bytes(int B, int H, size_t* bytes_out) {
   if (B <= 0 || H <= 0 || !bytes_out) return gr::set_error(GR_EINVAL, "lstm_workspace_bytes: bad argument");

@@ -14,6 +14,7 @@
 //            accumulator, apply hard_sigmoid/tanh, update c (registers), write y_t and publish
 //            h_t as bf16 hi/lo into the exchange buffer, then arrive on the step barrier.
 // CTAs of one (direction, batch tile) exchange h through L2 and a monotonic counter.
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace gr {
@@ -22,7 +23,7 @@ static constexpr int kTcThreads = 320;  // TMA warp, MMA warp, 8 epilogue warps
 static constexpr int kEU = 8;           // units per epilogue thread
 static constexpr int kUnits = 16;       // hidden units per CTA
 static constexpr int kNcols = 64;       // 4 gates x 16 units
-static constexpr int kStages = 2;
+static constexpr int kStages = 3;
 
 struct LstmTcParams {
   float* gates;       // (B, T, 8H): P in; post-activation gates out when save != 0
@@ -32,7 +33,10 @@ struct LstmTcParams {
   __nv_bfloat16* hb_lo;
   unsigned* counters;    // (2 dir, NBT) x 32
   int B, T, H, Bpad, Kp64, UGn, NBT, nchunks, save;
+  long long* trace;      // debug: per-step clock64 stamps of CTA 0 (GR_TC_TRACE), else null
 };
+
+#define TC_TRACE(slot, step) do { if (p.trace && blockIdx.x == 0 && (step) < 128) p.trace[(step) * 8 + (slot)] = clock64(); } while (0)
 
 __device__ __forceinline__ float hsig(float v) { return fminf(fmaxf(0.2f * v + 0.5f, 0.f), 1.f); }
 // tanh(x) = 1 - 2/(1 + e^{2x}) on MUFU ex2 + IEEE division: absolute error ~1e-7 (the libm tanhf
@@ -106,6 +110,7 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmHh, const __grid_consta
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
         } while (v < target);
         asm volatile("fence.proxy.async;" ::: "memory");
+        TC_TRACE(0, s);
         const int par_prev = (s + 1) & 1;
         const int row = (dir * 2 + par_prev) * p.Bpad + bt * 128;
         for (int c = 0; c < nch; ++c, ++it) {
@@ -117,6 +122,7 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmHh, const __grid_consta
           tma_load_2d(dst, &tmHh, &full[st], c * kBK, row);
           tma_load_2d(dst + a_bytes, &tmHl, &full[st], c * kBK, row);
         }
+        TC_TRACE(1, s);
       }
     }
   } else if (warp == 1) {
@@ -129,6 +135,7 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmHh, const __grid_consta
           const int st = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&full[st], ph);
+          if (c == 0) TC_TRACE(2, s);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_u32(stg + (size_t)st * 2 * a_bytes);
           const uint64_t dAh = make_sw128_desc(sa);
@@ -145,6 +152,7 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmHh, const __grid_consta
           umma_commit(&empty[st]);
         }
         umma_commit(tmem_full);
+        TC_TRACE(3, s);
       }
     }
   } else {
@@ -179,6 +187,7 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmHh, const __grid_consta
         }
       if (s > 0) {
         mbar_wait(tmem_full, (uint32_t)((s - 1) & 1));
+        if (threadIdx.x == 64) TC_TRACE(4, s);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t v[4][kEU];
 #pragma unroll
@@ -196,6 +205,7 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmHh, const __grid_consta
         for (int g = 0; g < 4; ++g)
 #pragma unroll
           for (int u = 0; u < kEU; ++u) pre[g][u] += __uint_as_float(v[g][u]);
+        if (threadIdx.x == 64) TC_TRACE(5, s);
       }
       float hv[kEU];
 #pragma unroll
@@ -227,10 +237,13 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmHh, const __grid_consta
           *reinterpret_cast<uint4*>(p.hb_lo + off) = make_uint4(lo_w[0], lo_w[1], lo_w[2], lo_w[3]);
         }
       }
+      if (threadIdx.x == 64) TC_TRACE(6, s);
       if (s + 1 < T) {
-        __threadfence();
+        // the release below is cumulative over everything ordered before it by bar.sync, so the
+        // 256 publishing threads do not each need a gpu-scope fence
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 64) TC_TRACE(7, s);
         if (threadIdx.x == 64) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
       }
       if (bok) {
@@ -268,7 +281,7 @@ int split_bf16_t_launch(const float* x, int R, int K, int ldx, __nv_bfloat16* hi
 
 struct TcLayout {
   int Bpad, Kp64, Kp8, UGn, NBT, nch;
-  size_t off_hb_hi, off_hb_lo, off_ut_hi, off_ut_lo, total;
+  size_t off_hb_hi, off_hb_lo, off_ut_hi, off_ut_lo, off_trace, total;
 };
 static TcLayout tc_layout(int B, int H) {
   TcLayout L;
@@ -285,11 +298,13 @@ static TcLayout tc_layout(int B, int H) {
   const size_t ut = (size_t)8 * H * L.Kp8 * 2;
   L.off_ut_hi = o; o += (ut + 255) & ~(size_t)255;
   L.off_ut_lo = o; o += (ut + 255) & ~(size_t)255;
+  L.off_trace = o; o += 128 * 8 * 8;
   L.total = o + 256;
   return L;
 }
 
 size_t lstm_tc_workspace_bytes(int B, int H) { return tc_layout(B, H).total; }
+size_t lstm_tc_trace_offset(int B, int H) { return tc_layout(B, H).off_trace; }
 
 bool lstm_tc_supported(int B, int H) {
   if (H % 4 != 0 || H < 32) return false;
@@ -308,6 +323,7 @@ int lstm_fwd_tc_launch(float* gates, const float* U, int B, int T, int H, float*
   p.hb_hi = reinterpret_cast<__nv_bfloat16*>(w + L.off_hb_hi);
   p.hb_lo = reinterpret_cast<__nv_bfloat16*>(w + L.off_hb_lo);
   p.counters = reinterpret_cast<unsigned*>(w);
+  p.trace = getenv("GR_TC_TRACE") ? reinterpret_cast<long long*>(w + L.off_trace) : nullptr;
   p.B = B; p.T = T; p.H = H; p.Bpad = L.Bpad; p.Kp64 = L.Kp64; p.UGn = L.UGn; p.NBT = L.NBT; p.nchunks = L.nch;
   GR_CUDA(cudaMemsetAsync(w, 0, L.off_ut_hi, s));  // counters + both exchange buffers
   __nv_bfloat16* ut_hi = reinterpret_cast<__nv_bfloat16*>(w + L.off_ut_hi);

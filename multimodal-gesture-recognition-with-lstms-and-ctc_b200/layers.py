@@ -20,21 +20,24 @@ from . import ops
 GEMM_PASSES = 3  # bf16x3 (fp32-faithful) tensor-core projections; 1 = plain bf16
 
 
-def _project(x2, W, b, masks, B, T, H, passes):
-    """Hoisted input projection P = X W + b  -> (B*T, 8H), on tcgen05."""
+def _project(x2, W, b, masks, B, T, H, passes=3):
+    """Hoisted input projection P = (X o mask_g) W_g + b -> (B*T, 8H) on tcgen05.  X stays fp32 in
+    HBM: masking and the bf16 hi/lo split are fused into the GEMM's producer warps."""
     BT, F = x2.shape
     gates = torch.empty((BT, 8 * H), dtype=torch.float32, device=x2.device)
-    wt_hi, wt_lo = ops.split_bf16(W, transpose=True, want_lo=passes == 3)  # (8H, pad8(F))
-    Kp = wt_hi.shape[1]
+    wt_hi, wt_lo = ops.split_bf16(W, transpose=True)  # (8H, pad8(F)): B operand, K-major
+    if F % 4:
+        # 39 MFCC / odd feature counts: zero-pad the (small) input to 16-byte rows so that the
+        # vectorised producer path applies; the padded weight columns are zero as well
+        Fp = (F + 3) // 4 * 4
+        x2 = torch.nn.functional.pad(x2, (0, Fp - F))
+        if masks is not None:
+            masks = torch.nn.functional.pad(masks, (0, Fp - F))
+        F = Fp
     if masks is None:
-        a_hi, a_lo = ops.split_bf16(x2, want_lo=passes == 3)
-        ops.gemm_nt(a_hi, a_lo, wt_hi, wt_lo, BT, 8 * H, Kp, out=gates, ldc=8 * H, bias=b, passes=passes)
+        ops.gemm_a32(x2, wt_hi, wt_lo, BT, 8 * H, F, gates, 8 * H, bias=b)
     else:
-        for dg in range(8):
-            n0 = dg * H
-            a_hi, a_lo = ops.split_bf16(x2, mask=masks[dg], rows_per_seq=T, want_lo=passes == 3)
-            ops.gemm_nt(a_hi, a_lo, wt_hi[n0:n0 + H], None if wt_lo is None else wt_lo[n0:n0 + H], BT, H, Kp,
-                        out=gates, ldc=8 * H, bias=b[n0:n0 + H], passes=passes, out_col_offset=n0)
+        ops.gemm_a32(x2, wt_hi, wt_lo, BT, H, F, gates, 8 * H, nvar=8, mask=masks, rows_per_seq=T, bias=b)
     return gates
 
 
@@ -48,60 +51,50 @@ class _BlstmFn(torch.autograd.Function):
         masks = None if masks is None else masks.contiguous()
         x2 = x.reshape(B * T, F)
         need_grad = any(ctx.needs_input_grad[:4])
-        gates = _project(x2, W, b, masks, B, T, H, passes)
+        gates = _project(x2, W, b, masks, B, T, H)
         y, cell = ops.lstm_recurrence_fwd(gates, U, B, T, H, keep_cell=need_grad)
         if need_grad:
             ctx.save_for_backward(x, W, U, masks, gates, cell, y)
-            ctx.passes = passes
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, W, U, masks, gates, cell, y = ctx.saved_tensors
-        passes = ctx.passes
         B, T, F = x.shape
         H = U.shape[1]
         BT = B * T
-        lo = passes == 3
         dP = ops.lstm_recurrence_bwd(gates, cell, dy.contiguous(), U, B, T, H).reshape(BT, 8 * H)
         x2 = x.reshape(BT, F)
         y2 = y.reshape(BT, 2 * H)
         db = ops.colsum(dP) if ctx.needs_input_grad[3] else None
         dW = dU = dx = None
-        dpt_hi, dpt_lo = ops.split_bf16(dP, transpose=True, want_lo=lo)  # (8H, pad8(BT))
-        Kbt = dpt_hi.shape[1]
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dpt_hi, dpt_lo = ops.split_bf16(dP, transpose=True)  # dP^T (8H, pad8(BT)): B operand of dW and dU
         if ctx.needs_input_grad[1]:
+            # dW_g = (X o mask_g)^T dP_g : A = X read transposed by the producer warps
             dW = torch.empty((F, 8 * H), dtype=torch.float32, device=x.device)
             if masks is None:
-                xt_hi, xt_lo = ops.split_bf16(x2, transpose=True, want_lo=lo)
-                ops.gemm_nt(xt_hi, xt_lo, dpt_hi, dpt_lo, F, 8 * H, Kbt, out=dW, ldc=8 * H, passes=passes)
+                ops.gemm_a32(x2, dpt_hi, dpt_lo, F, 8 * H, BT, dW, 8 * H, transA=True, rows_per_seq=T)
             else:
-                for dg in range(8):
-                    n0 = dg * H
-                    xt_hi, xt_lo = ops.split_bf16(x2, mask=masks[dg], rows_per_seq=T, transpose=True, want_lo=lo)
-                    ops.gemm_nt(xt_hi, xt_lo, dpt_hi[n0:n0 + H], None if dpt_lo is None else dpt_lo[n0:n0 + H],
-                                F, H, Kbt, out=dW, ldc=8 * H, passes=passes, out_col_offset=n0)
+                ops.gemm_a32(x2, dpt_hi, dpt_lo, F, H, BT, dW, 8 * H, nvar=8, mask=masks, rows_per_seq=T, transA=True)
         if ctx.needs_input_grad[2]:
+            # dU_d = H_prev^T dP_d : A = y shifted by one step inside each sequence
             dU = torch.empty((2, H, 4 * H), dtype=torch.float32, device=x.device)
             for d in range(2):
-                hp_hi, hp_lo = ops.split_bf16(y2, rows_per_seq=T, transpose=True, row_shift=-1 if d == 0 else 1,
-                                              ncols=H, col_offset=d * H, want_lo=lo)
-                ops.gemm_nt(hp_hi, hp_lo, dpt_hi[d * 4 * H:(d + 1) * 4 * H],
-                            None if dpt_lo is None else dpt_lo[d * 4 * H:(d + 1) * 4 * H], H, 4 * H, Kbt,
-                            out=dU[d], ldc=4 * H, passes=passes)
+                ops.gemm_a32(y2, dpt_hi[d * 4 * H:(d + 1) * 4 * H], dpt_lo[d * 4 * H:(d + 1) * 4 * H], H, 4 * H, BT,
+                             dU[d], 4 * H, transA=True, rows_per_seq=T, row_shift=-1 if d == 0 else 1,
+                             a_col_offset=d * H)
         if ctx.needs_input_grad[0]:
             dx2 = torch.empty((BT, F), dtype=torch.float32, device=x.device)
             if masks is None:
-                dp_hi, dp_lo = ops.split_bf16(dP, want_lo=lo)
-                w_hi, w_lo = ops.split_bf16(W, want_lo=lo)
-                ops.gemm_nt(dp_hi, dp_lo, w_hi, w_lo, BT, F, dp_hi.shape[1], out=dx2, ldc=F, passes=passes)
+                w_hi, w_lo = ops.split_bf16(W)  # (F, 8H) K-major
+                ops.gemm_a32(dP, w_hi, w_lo, BT, F, 8 * H, dx2, F)
             else:
                 tmp = torch.empty((BT, F), dtype=torch.float32, device=x.device)
                 for dg in range(8):
                     n0 = dg * H
-                    dp_hi, dp_lo = ops.split_bf16(dP, ncols=H, col_offset=n0, want_lo=lo)
-                    w_hi, w_lo = ops.split_bf16(W, ncols=H, col_offset=n0, want_lo=lo)
-                    ops.gemm_nt(dp_hi, dp_lo, w_hi, w_lo, BT, F, dp_hi.shape[1], out=tmp, ldc=F, passes=passes)
+                    w_hi, w_lo = ops.split_bf16(W, ncols=H, col_offset=n0)
+                    ops.gemm_a32(dP, w_hi, w_lo, BT, F, H, tmp, F, a_col_offset=n0)
                     ops.mask_mul_acc(dx2, tmp, masks[dg], T, accumulate=dg > 0)
             dx = dx2.reshape(B, T, F)
         return dx, dW, dU, db, None, None

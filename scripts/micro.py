@@ -26,4 +26,18 @@ elif what == "gemm":
     a = ops.split_bf16(x); w = ops.split_bf16(W, transpose=True)
     for _ in range(2):
         ops.gemm_nt(a[0], a[1], w[0], w[1], M, N, K)
+elif what == "a32":
+    BT, T, F, H = 65536, 1000, 1000, 500
+    x = torch.randn(BT, F, device=dev); W = torch.randn(F, 8 * H, device=dev) * 0.05; b = torch.zeros(8 * H, device=dev)
+    masks = ((torch.rand(8, BT // T + 1, F, device=dev) > 0.5).float() * 2)[:, :BT // T + 1].contiguous()
+    for _ in range(2):
+        layers._project(x, W, b, masks, BT // T, T, H)
+elif what == "a32t":
+    BT, T, F, H = 65536, 1000, 1600, 100
+    x = torch.randn(BT, F, device=dev); dP = torch.randn(BT, 8 * H, device=dev)
+    masks = ((torch.rand(8, BT // T + 1, F, device=dev) > 0.5).float() * 2).contiguous()
+    pt = ops.split_bf16(dP, transpose=True)
+    dW = torch.empty(F, 8 * H, device=dev)
+    for _ in range(2):
+        ops.gemm_a32(x, pt[0], pt[1], F, H, BT, dW, 8 * H, nvar=8, mask=masks, rows_per_seq=T, transA=True)
 torch.cuda.synchronize()

@@ -67,3 +67,67 @@ def test_row_shift_split(cuda):
     ref = torch.zeros(B, T, H, device=cuda)
     ref[:, 1:] = y.reshape(B, T, 2 * H)[:, :-1, H:]
     assert torch.allclose(got, ref, atol=1e-6)
+
+
+@pytest.mark.parametrize("BT,T,F,H,nvar", [(96, 12, 64, 32, 8), (200, 25, 39, 20, 8), (384, 48, 1600, 100, 8),
+                                           (300, 30, 20, 300, 1), (256, 16, 1000, 500, 8),
+                                           (1000, 200, 1600, 100, 8), (768, 128, 40, 500, 8), (1300, 650, 600, 300, 8),
+                                           (900, 300, 1000, 500, 1)])
+def test_fused_prologue_projection(cuda, BT, T, F, H, nvar):
+    """gr_gemm_a32_f32, transA=0: P[:, v*H:(v+1)*H] = (X o mask_v) W_v + b with X read as fp32."""
+    from mgr_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(BT + F)
+    X = torch.randn(BT, F, generator=g).to(cuda)
+    Nv = H if nvar == 8 else 8 * H
+    W = (torch.randn(F, nvar * Nv, generator=g) * 0.1).to(cuda)
+    bias = torch.randn(nvar * Nv, generator=g).to(cuda)
+    masks = ((torch.rand(nvar, BT // T, F, generator=g) > 0.5).float() * 2).to(cuda) if nvar == 8 else None
+    w_hi, w_lo = ops.split_bf16(W, transpose=True)
+    out = torch.empty(BT, nvar * Nv, device=cuda)
+    ops.gemm_a32(X, w_hi, w_lo, BT, Nv, F, out, nvar * Nv, nvar=nvar, mask=masks, rows_per_seq=T, bias=bias)
+    torch.cuda.synchronize()
+    Xd, Wd = X.double(), W.double()
+    if masks is None:
+        ref = Xd @ Wd + bias.double()
+    else:
+        ref = torch.cat([(Xd.reshape(-1, T, F) * masks[v].double()[:, None, :]).reshape(BT, F) @ Wd[:, v * Nv:(v + 1) * Nv]
+                         for v in range(nvar)], 1) + bias.double()
+    assert (out.double() - ref).abs().max().item() <= 3e-5 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("BT,T,F,H,masked", [(256, 32, 64, 32, True), (1024, 64, 1600, 100, True), (600, 50, 39, 24, False),
+                                             (4096, 128, 200, 100, True), (3000, 1000, 1600, 100, True),
+                                             (2000, 100, 77, 36, True), (1500, 500, 600, 300, False)])
+def test_fused_prologue_weight_gradient(cuda, BT, T, F, H, masked):
+    """transA=1: dW_v = (X o mask_v)^T dP_v (split-K, atomics) and the shifted dU contraction."""
+    from mgr_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(BT + F + 1)
+    X = torch.randn(BT, F, generator=g).to(cuda)
+    dP = torch.randn(BT, 8 * H, generator=g).to(cuda)
+    masks = ((torch.rand(8, BT // T, F, generator=g) > 0.5).float() * 2).to(cuda) if masked else None
+    pt_hi, pt_lo = ops.split_bf16(dP, transpose=True)
+    dW = torch.empty(F, 8 * H, device=cuda)
+    if masked:
+        ops.gemm_a32(X, pt_hi, pt_lo, F, H, BT, dW, 8 * H, nvar=8, mask=masks, rows_per_seq=T, transA=True)
+        ref = torch.cat([(X.double().reshape(-1, T, F) * masks[v].double()[:, None, :]).reshape(BT, F).T
+                         @ dP.double()[:, v * H:(v + 1) * H] for v in range(8)], 1)
+    else:
+        ops.gemm_a32(X, pt_hi, pt_lo, F, 8 * H, BT, dW, 8 * H, transA=True, rows_per_seq=T)
+        ref = X.double().T @ dP.double()
+    torch.cuda.synchronize()
+    assert (dW.double() - ref).abs().max().item() <= 3e-5 * ref.abs().max().item()
+    # dU_d = Hprev^T dP_d with the time shift inside each sequence
+    Y = torch.randn(BT, 2 * H, generator=g).to(cuda)
+    for d, shift in ((0, -1), (1, 1)):
+        dU = torch.empty(H, 4 * H, device=cuda)
+        ops.gemm_a32(Y, pt_hi[d * 4 * H:(d + 1) * 4 * H], pt_lo[d * 4 * H:(d + 1) * 4 * H], H, 4 * H, BT, dU, 4 * H,
+                     transA=True, rows_per_seq=T, row_shift=shift, a_col_offset=d * H)
+        Y3 = Y.double().reshape(-1, T, 2 * H)[:, :, d * H:(d + 1) * H]
+        Hp = torch.zeros_like(Y3)
+        if shift == -1:
+            Hp[:, 1:] = Y3[:, :-1]
+        else:
+            Hp[:, :-1] = Y3[:, 1:]
+        refU = Hp.reshape(BT, H).T @ dP.double()[:, d * 4 * H:(d + 1) * 4 * H]
+        torch.cuda.synchronize()
+        assert (dU.double() - refU).abs().max().item() <= 3e-5 * refU.abs().max().item()
