@@ -63,15 +63,14 @@ __global__ void __launch_bounds__(64) ctc_loss_grad_kernel(CtcParams p) {
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = p.C, T = p.T, Lmax = p.Lmax, RS = p.RS;
-  const int Cp = ctc_cp(C), RSp = ctc_rsp(RS);
   const int blank = C - 1;
   // smem carve-up: [labs Lmax ints][logp broadcast 4 floats] then per warp: Xs, Os, Es
   int* labs = reinterpret_cast<int*>(smem);
   float* bcast = smem + ((Lmax + 3) & ~3);
-  float* wbase = bcast + 4 + warp * (2 * TC * Cp + TC * RSp);
-  float* Xs = wbase;
-  float* Os = Xs + TC * Cp;
-  float* Es = Os + TC * Cp;
+  float* wbase = bcast + 4 + warp * (3 * TC * C + 2 * TC * RS);
+  float* Xs = wbase;                 // 2 buffers x TC rows x C
+  float* Os = Xs + 2 * TC * C;       // TC x C
+  float* Es = Os + TC * C;           // 2 buffers x TC rows x RS (RS odd: conflict-free lane-per-row)
 
   const float* xb = p.x + (size_t)b * T * C;
   float* gb = p.grad ? p.grad + (size_t)b * T * C : nullptr;
@@ -156,6 +155,23 @@ __global__ void __launch_bounds__(64) ctc_loss_grad_kernel(CtcParams p) {
 #pragma unroll
   for (int j = 0; j < K; ++j) lpl_last[j] = kNeg;
 
+  // shared-memory staging: two buffers per warp, filled by cp.async one chunk ahead
+  auto stage_chunk = [&](int buf, int tlo, int n, bool with_lattice) {
+    const float* src = xb + (size_t)(p.drop + tlo) * C;
+    float* dx = Xs + buf * (TC * C);
+    const int tot = n * C;
+    for (int e = lane; e < tot; e += 32)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dx + e)), "l"(src + e) : "memory");
+    if (with_lattice) {
+      const float* lsrc = other_rows + (size_t)tlo * RS;
+      float* de = Es + buf * (TC * RS);
+      const int ltot = n * RS;
+      for (int e = lane; e < ltot; e += 32)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(de + e)), "l"(lsrc + e) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
   for (int phase = 0; phase < 2; ++phase) {
     if (phase == 1 && p.grad == nullptr) break;
     // processing-order step range of this phase
@@ -164,50 +180,31 @@ __global__ void __launch_bounds__(64) ctc_loss_grad_kernel(CtcParams p) {
     if (phase == 0) { i_begin = 0; i_end = dir == 0 ? tstar + 1 : Tn - tstar; }
     else if (dir == 0) { i_begin = tstar; i_end = Tn; hold_first = true; }
     else { i_begin = Tn - tstar; i_end = Tn; }
+    const bool lat = phase == 1;
+    const int nchunks = (i_end - i_begin + TC - 1) / TC;
+    auto chunk_range = [&](int ci, int& ic, int& ie, int& tlo) {
+      ic = i_begin + ci * TC;
+      ie = min(ic + TC, i_end);
+      tlo = dir == 0 ? ic : Tn - ie;
+    };
+    if (nchunks > 0) { int ic, ie, tlo; chunk_range(0, ic, ie, tlo); stage_chunk(0, tlo, ie - ic, lat); }
 
-    for (int ic = i_begin; ic < i_end; ic += TC) {
-      const int ie = min(ic + TC, i_end);
+    for (int ci = 0; ci < nchunks; ++ci) {
+      int ic, ie, tlo;
+      chunk_range(ci, ic, ie, tlo);
       const int n = ie - ic;
-      const int tlo = dir == 0 ? ic : Tn - ie;
-      // ---- stage the probability rows [tlo, tlo+n)
-      {
-        const float* src = xb + (size_t)(p.drop + tlo) * C;
-        const int tot = n * C;
-        int r = lane / C, c = lane - r * C;  // lane < 32 <= ... handle C < 32 generally below
-        for (int e = lane; e < tot; e += 32) {
-          r = e / C; c = e - r * C;
-          Xs[r * Cp + c] = __ldg(src + e);
-        }
-        if (phase == 1) {
-          const float* lsrc = other_rows + (size_t)tlo * RS;
-          const int ltot = n * RS;
-          for (int e = lane; e < ltot; e += 32) {
-            const int rr = e / RS, s = e - rr * RS;
-            Es[rr * RSp + s] = lsrc[e];
-          }
-        }
+      const int buf = ci & 1;
+      if (ci + 1 < nchunks) {
+        int ic2, ie2, tlo2;
+        chunk_range(ci + 1, ic2, ie2, tlo2);
+        stage_chunk(buf ^ 1, tlo2, ie2 - ic2, lat);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
       }
       __syncwarp();
-      // ---- per-row pre-pass: lp2 = log2 q, q = softmax(log(p + eps)) = (p+eps)/sum(p+eps)
-      float Zrow = 1.f;
-      if (lane < n) {
-        float* row = Xs + lane * Cp;
-        float Z = 0.f;
-        if (p.is_logits) {
-          float m = row[0];
-          for (int c = 1; c < C; ++c) m = fmaxf(m, row[c]);
-          float s = 0.f;
-          for (int c = 0; c < C; ++c) { float e_ = ex2_approx((row[c] - m) * kLog2e); row[c] = e_; s += e_; }
-          const float inv = 1.0f / s;
-          for (int c = 0; c < C; ++c) { float pe = row[c] * inv + eps; row[c] = pe; Z += pe; }
-        } else {
-          for (int c = 0; c < C; ++c) { float pe = row[c] + eps; row[c] = pe; Z += pe; }
-        }
-        const float lz = lg2_approx(Z);
-        for (int c = 0; c < C; ++c) row[c] = fmaxf(lg2_approx(row[c]) - lz, kNeg);
-        Zrow = Z;
-      }
-      __syncwarp();
+      float* Xc = Xs + buf * (TC * C);
+      float* Ec = Es + buf * (TC * RS);
       // ---- re-centre the states on their maximum (once per chunk; uniform across the warp)
       if (ic > 0) {
         float mx = kNeg;
@@ -216,45 +213,71 @@ __global__ void __launch_bounds__(64) ctc_loss_grad_kernel(CtcParams p) {
         mx = warp_max(mx);
         if (mx > -1.0e29f) {
 #pragma unroll
-          for (int j = 0; j < K; ++j) {
-            sb[j] = fmaxf(sb[j] - mx, kNeg);
-            sl[j] = fmaxf(sl[j] - mx, kNeg);
-          }
+          for (int j = 0; j < K; ++j) { sb[j] -= mx; sl[j] -= mx; }
           off += (double)mx;
         }
       }
       const float off_hi = (float)off, off_lo = (float)(off - (double)off_hi);
+      // ---- per-row pre-pass: lp2 = log2 q, q = softmax(log(p + eps)) = (p+eps)/sum(p+eps);
+      //      phase 1 also folds (my offset + other offset - log p) into the row's last slot
+      float Zrow = 1.f;
+      if (lane < n) {
+        float* row = Xc + lane * C;
+        float Z = 0.f;
+        if (p.is_logits) {
+          float m = row[0];
+          for (int c = 1; c < C; ++c) m = fmaxf(m, row[c]);
+          float s_ = 0.f;
+          for (int c = 0; c < C; ++c) { float e_ = ex2_approx((row[c] - m) * kLog2e); row[c] = e_; s_ += e_; }
+          const float inv = 1.0f / s_;
+          for (int c = 0; c < C; ++c) { float pe = row[c] * inv + eps; row[c] = pe; Z += pe; }
+        } else {
+          for (int c = 0; c < C; ++c) { float pe = row[c] + eps; row[c] = pe; Z += pe; }
+        }
+        const float lz = lg2_approx(Z);
+        for (int c = 0; c < C; ++c) row[c] = fmaxf(lg2_approx(row[c]) - lz, kNeg);
+        Zrow = Z;
+        if (lat) {
+          float* erow = Ec + lane * RS;
+          erow[RS - 1] = novalid ? kNeg : (float)(off + (double)erow[RS - 2] + (double)erow[RS - 1] - logp2);
+        }
+      }
+      __syncwarp();
       // ---- the serial part
-      for (int i = ic; i < ie; ++i) {
-        const int r = dir == 0 ? i - ic : ie - 1 - i;
-        const float* row = Xs + r * Cp;
+      int i = ic;
+      if (i == 0) {  // initial state of the recursion (phase 0 only)
+        const float* row = Xc + (dir == 0 ? 0 : n - 1) * C;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const int k = lane * K + j;
+          sb[j] = (k == 0) ? row[blank] : kNeg;
+          sl[j] = (k == 0 && vl[j]) ? row[labr[j]] : kNeg;
+        }
+      }
+      const int rstep = dir == 0 ? 1 : -1;
+      int r = dir == 0 ? 0 : n - 1;
+      float* dst = my_rows + (size_t)(dir == 0 ? ic : Tn - 1 - ic) * RS;
+      const int dstep = dir == 0 ? RS : -RS;
+      for (; i < ie; ++i, r += rstep, dst += dstep) {
+        const float* row = Xc + r * C;
         const float lpb = row[blank];
         float lpl[K];
 #pragma unroll
         for (int j = 0; j < K; ++j) lpl[j] = vl[j] ? row[labr[j]] : kNeg;
-        if (i == 0) {
-#pragma unroll
-          for (int j = 0; j < K; ++j) {
-            const int k = lane * K + j;
-            sb[j] = (k == 0) ? lpb : kNeg;
-            sl[j] = (k == 0 && vl[j]) ? lpl[j] : kNeg;
-          }
-        } else if (!(hold_first && i == i_begin)) {
+        if (i != 0 && !(hold_first && i == i_begin)) {
           float upv = __shfl_up_sync(0xffffffffu, sl[K - 1], 1);
           if (lane == 0) upv = kNeg;
           float nb[K], nl[K];
 #pragma unroll
           for (int j = 0; j < K; ++j) {
             const float prevl = (j == 0) ? upv : sl[j - 1];
-            nb[j] = vb[j] ? lse2(sb[j], prevl) + lpb : kNeg;
-            nl[j] = vl[j] ? lse3(sl[j], sb[j], skip[j] ? prevl : kNeg) + lpl[j] : kNeg;
+            nb[j] = lse2(sb[j], prevl) + (vb[j] ? lpb : kNeg);
+            nl[j] = lse3(sl[j], sb[j], skip[j] ? prevl : kNeg) + lpl[j];
           }
 #pragma unroll
-          for (int j = 0; j < K; ++j) { sb[j] = fmaxf(nb[j], kNeg); sl[j] = fmaxf(nl[j], kNeg); }
+          for (int j = 0; j < K; ++j) { sb[j] = nb[j]; sl[j] = nl[j]; }
         }
-        if (phase == 0) {
-          const int t = dir == 0 ? i : Tn - 1 - i;
-          float* dst = my_rows + (size_t)t * RS;
+        if (!lat) {
 #pragma unroll
           for (int j = 0; j < K; ++j) {
             if (vb[j]) dst[posb[j]] = sb[j];
@@ -267,23 +290,22 @@ __global__ void __launch_bounds__(64) ctc_loss_grad_kernel(CtcParams p) {
             for (int j = 0; j < K; ++j) lpl_last[j] = lpl[j];
           }
         } else {
-          float* erow = Es + r * RSp;
-          // (my offset + the other direction's offset at this row - log p): small, formed in double
-          const float cst = (float)(off + (double)erow[RS - 2] + (double)erow[RS - 1] - logp2);
+          float* erow = Ec + r * RS;
+          const float cst = erow[RS - 1];
 #pragma unroll
           for (int j = 0; j < K; ++j) {
-            if (vb[j]) erow[posb[j]] = novalid ? 0.f : ex2_approx((sb[j] + erow[posb[j]] - lpb) + cst);
-            if (vl[j]) erow[posl[j]] = novalid ? 0.f : ex2_approx((sl[j] + erow[posl[j]] - lpl[j]) + cst);
+            if (vb[j]) erow[posb[j]] = ex2_approx((sb[j] + erow[posb[j]] - lpb) + cst);
+            if (vl[j]) erow[posl[j]] = ex2_approx((sl[j] + erow[posl[j]] - lpl[j]) + cst);
           }
         }
       }
-      if (phase == 1) {
+      if (lat) {
         __syncwarp();
-        // ---- per-row post-pass: occupancies -> gradient, in place in Xs
+        // ---- per-row post-pass: occupancies -> gradient
         if (lane < n) {
-          float* row = Xs + lane * Cp;
-          float* orow = Os + lane * Cp;
-          const float* erow = Es + lane * RSp;
+          const float* row = Xc + lane * C;
+          float* orow = Os + lane * C;
+          const float* erow = Ec + lane * RS;
           for (int c = 0; c < C; ++c) orow[c] = 0.f;
           float occb = 0.f;
           for (int k = 0; k <= L; ++k) occb += erow[k];
@@ -304,22 +326,19 @@ __global__ void __launch_bounds__(64) ctc_loss_grad_kernel(CtcParams p) {
             for (int c = 0; c < C; ++c) {
               const float q = ex2_approx(row[c]);
               const float pr = fmaxf(q * Z - eps, 0.f);
-              row[c] = orow[c] - pr * dot;
+              orow[c] = orow[c] - pr * dot;
             }
           } else {
             for (int c = 0; c < C; ++c) {
               const float q = ex2_approx(row[c]);
-              row[c] = up_scale * (q - orow[c]) / (q * Z);
+              orow[c] = up_scale * __fdividef(q - orow[c], q * Z);
             }
           }
         }
         __syncwarp();
-        float* dst = gb + (size_t)(p.drop + tlo) * C;
+        float* gdst = gb + (size_t)(p.drop + tlo) * C;
         const int tot = n * C;
-        for (int e = lane; e < tot; e += 32) {
-          const int r = e / C, c = e - r * C;
-          dst[e] = Xs[r * Cp + c];
-        }
+        for (int e = lane; e < tot; e += 32) gdst[e] = Os[e];
         __syncwarp();
       }
     }
@@ -336,11 +355,11 @@ __global__ void __launch_bounds__(64) ctc_loss_grad_kernel(CtcParams p) {
           m = fmaxf(m, fmaxf(v[2 * j], v[2 * j + 1]));
         }
         m = warp_max(m);
-        float s = 0.f;
+        float s_ = 0.f;
 #pragma unroll
-        for (int j = 0; j < 2 * K; ++j) s += ex2_approx(v[j] - m);
-        s = warp_sum(s);
-        const float lp2 = m + lg2_approx(s);
+        for (int j = 0; j < 2 * K; ++j) s_ += ex2_approx(v[j] - m);
+        s_ = warp_sum(s_);
+        const float lp2 = m + lg2_approx(s_);
         if (lane == 0) {
           const bool nv = !(m > -1.0e29f) || !(lp2 > -1.0e29f);
           double* bd = reinterpret_cast<double*>(bcast);
@@ -359,10 +378,10 @@ __global__ void __launch_bounds__(64) ctc_loss_grad_kernel(CtcParams p) {
 }
 
 static size_t ctc_smem_bytes(int C, int Lmax, int RS, int TC) {
-  size_t fl = ((Lmax + 3) & ~3) + 4 + 2 * (size_t)(2 * TC * ctc_cp(C) + TC * ctc_rsp(RS));
+  size_t fl = ((Lmax + 3) & ~3) + 4 + 2 * (size_t)(3 * TC * C + 2 * TC * RS);
   return fl * sizeof(float);
 }
-static int ctc_row_stride(int Lmax) { return (2 * Lmax + 3 + 7) & ~7; }  // +2: per-row offset (hi, lo)
+static int ctc_row_stride(int Lmax) { return (2 * Lmax + 3) | 1; }  // +2: per-row offset (hi, lo); odd stride
 
 template <int K>
 static int launch_ctc(const CtcParams& p, cudaStream_t stream) {
