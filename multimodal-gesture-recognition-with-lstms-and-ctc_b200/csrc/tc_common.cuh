@@ -95,5 +95,20 @@ static inline int make_map(CUtensorMap* tm, const void* base, uint64_t rows, uin
   return GR_OK;
 }
 
+// General tiled map: dims / box innermost first, strides (bytes) of dims 1..rank-1; strides need not
+// be ascending (the LSTM recurrence declares (unit, batch row, time, gate) over a (B, T, 8H) tensor).
+static inline int make_map_nd(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,
+                              const cuuint64_t* strides, const cuuint32_t* box, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(GR_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(tm, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled(rank %d) failed: %d", rank, (int)r);
+    return GR_ECUDA;
+  }
+  return GR_OK;
+}
 
 }  // namespace gr

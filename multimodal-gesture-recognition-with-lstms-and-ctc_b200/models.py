@@ -98,6 +98,7 @@ class FusionNet(nn.Module):
                 p.requires_grad_(False)
         fin = 2 * self.speech.units + 2 * self.skeletal.units
         self.units, self.nb_classes = units, nb_classes
+        self._streams = None
         self.blstm_3 = BidirectionalLSTM(fin, units, dropout=0.5, seed=seed, name="blstm_2")
         self.dense = DenseSoftmax(2 * units, nb_classes, seed=seed)
 
@@ -121,8 +122,20 @@ class FusionNet(nn.Module):
     def merged(self, xa, xs, reg=None):
         reg = reg or {}
         with torch.no_grad():
-            ra = self.speech.tower(xa, reg.get("sp"))
-            rs = self.skeletal.tower(xs, reg.get("sk"))
+            # the two towers are independent until the concat (multimodal.py:109-118,155): run them on
+            # two streams -- their recurrences (64 + 40 persistent CTAs) and GEMMs overlap on the 148 SMs
+            cur = torch.cuda.current_stream()
+            if self._streams is None:
+                self._streams = (torch.cuda.Stream(), torch.cuda.Stream())
+            sa, sb = self._streams
+            sa.wait_stream(cur)
+            sb.wait_stream(cur)
+            with torch.cuda.stream(sa):
+                ra = self.speech.tower(xa, reg.get("sp"))
+            with torch.cuda.stream(sb):
+                rs = self.skeletal.tower(xs, reg.get("sk"))
+            cur.wait_stream(sa)
+            cur.wait_stream(sb)
             return ops.concat2(ra, rs)
 
     def forward(self, xa, xs, reg=None):
