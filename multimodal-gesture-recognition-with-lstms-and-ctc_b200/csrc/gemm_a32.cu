@@ -11,12 +11,23 @@
 // (K, M) -- the X^T / H_prev^T operands of the BPTT weight-gradient contractions -- with an
 // optional time shift inside each sequence (h_{t-1} / h_{t+1} pairing for dU).
 // B (weights, or dP^T) arrives pre-split through TMA.  Arithmetic: bf16x3, fp32 accumulate.
+//
+// PERSISTENT: grid = #SMs, every CTA walks output tiles (M-tile major, so the CTAs running at the
+// same time share their fp32 A rows in L2) with one continuous smem ring and TWO TMEM accumulators:
+//   warp 0      TMA of the B k-blocks            warp 1      tcgen05.mma issue (one elected lane,
+//   warps 2-9   A producers                                  warp-uniform operands)
+//   warps 10-13 epilogue of tile i (tcgen05.ld -> +bias -> swizzled smem -> TMA tensor store, or
+//               fp32 atomics for split-K / accumulate) while the other warps are on tile i+1.
+// The K = 39 / 20 first-layer projections are a pure 4 GB store stream: one CTA per tile spent
+// ~50 k cycles per tile on launch, TMEM allocation and per-thread-row stores (32 lines per warp
+// store instruction); see profiles/r01_gemm_a32_*.
 #include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace gr {
 
-static constexpr int kA32Threads = 320;  // TMA warp, MMA warp, 8 producer/epilogue warps
+static constexpr int kA32Threads = 448;  // TMA warp, MMA warp, 8 A-producer warps, 4 epilogue warps
+static constexpr uint32_t kEpiStage = 16384;   // 128 rows x 32 fp32, SWIZZLE_128B, two buffers
 
 struct A32Params {
   const float* A;
@@ -26,7 +37,20 @@ struct A32Params {
   long long mask_var_stride;
   int lda, ldc, M, Nv, K, BN, nvar, ntile, rows_per_seq, row_shift, transA, aligned4;
   int kb_total, kb_per_split, stages, use_atomic, tmem_cols;
+  long long* trace;     // debug (GR_A32_TRACE): clock64 stamps [cta][k-block < 64][8]
+  int splits, tiles_n, ntiles_total;   // tile t = ((m tile * tiles_n) + (variant, n tile)) * splits + k split
 };
+
+#define A32_TRACE(slot, it) do { if (p.trace && (it) < 64) p.trace[((size_t)blockIdx.x * 64 + (it)) * 8 + (slot)] = clock64(); } while (0)
+__device__ __forceinline__ bool a32_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void a32_tma_store_3d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 
 __device__ __forceinline__ void split2(float v, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -48,31 +72,38 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
 // MODE 2: fast transposed A  (a 64-row k-block spans <= 2 sequences)
 template <int MODE>
 __global__ void __launch_bounds__(kA32Threads, 1)
-gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, A32Params p) {
+gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                const __grid_constant__ CUtensorMap tmC, A32Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int BN = p.BN;
   const uint32_t a_bytes = 128 * kBK * 2;
   const uint32_t b_bytes = (uint32_t)BN * kBK * 2;
-  const uint32_t stage_bytes = 2 * (a_bytes + b_bytes);
-  uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  const uint32_t stage_bytes = 2 * (a_bytes + b_bytes);     // a multiple of 1024 (BN % 16 == 0)
+  uint8_t* epi = smem + (size_t)p.stages * stage_bytes;     // 2 x kEpiStage
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(epi + 2 * kEpiStage);
   uint64_t* fullB = fullA + p.stages;
   uint64_t* empty = fullB + p.stages;
-  uint64_t* tmem_full = empty + p.stages;
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + p.stages;    // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int var = blockIdx.x / p.ntile, nt = blockIdx.x % p.ntile;
-  const int m0 = blockIdx.y * 128, n0 = nt * BN;
-  const int kb_begin = blockIdx.z * p.kb_per_split;
-  const int kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
-  const int nkb = kb_end - kb_begin;
+  // tile decode (identical in every role): t -> (m0, var, n0, k-block range)
+#define A32_TILE_DECODE(t)                                                    \
+  const int z_ = (t) % p.splits;                                              \
+  const int nv_ = ((t) / p.splits) % p.tiles_n;                               \
+  const int m0 = ((t) / p.splits / p.tiles_n) * 128;                          \
+  const int var = nv_ / p.ntile, n0 = (nv_ % p.ntile) * BN;                   \
+  const int kb_begin = z_ * p.kb_per_split;                                   \
+  const int nkb = min(kb_begin + p.kb_per_split, p.kb_total) - kb_begin;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBh)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBl)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(&fullA[s], 256); mbar_init(&fullB[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -85,46 +116,72 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr_s;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % p.stages;
-        const uint32_t ph = (i / p.stages) & 1;
+    // ---- B operand: two TMA requests (hi, lo) per k-block; the whole warp runs the loop with
+    // warp-uniform operands, one elected lane issues (no R2UR waterfall around UTMALDG)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles_total; tile += gridDim.x) {
+      A32_TILE_DECODE(tile)
+      (void)m0;
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* st = smem + (size_t)s * stage_bytes + 2 * a_bytes;
-        mbar_expect_tx(&fullB[s], 2 * b_bytes);
-        const int k0 = (kb_begin + i) * kBK;
-        tma_load_2d(st, &tmBh, &fullB[s], k0, var * p.Nv + n0);
-        tma_load_2d(st + b_bytes, &tmBl, &fullB[s], k0, var * p.Nv + n0);
+        if (lane == 0) A32_TRACE(6, it);
+        if (a32_elect_one()) {
+          uint8_t* st = smem + (size_t)s * stage_bytes + 2 * a_bytes;
+          mbar_expect_tx(&fullB[s], 2 * b_bytes);
+          const int k0 = (kb_begin + i) * kBK;
+          tma_load_2d(st, &tmBh, &fullB[s], k0, var * p.Nv + n0);
+          tma_load_2d(st + b_bytes, &tmBl, &fullB[s], k0, var * p.Nv + n0);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % p.stages;
-        const uint32_t ph = (i / p.stages) & 1;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles_total; tile += gridDim.x, ++lt) {
+      A32_TILE_DECODE(tile)
+      (void)m0; (void)var; (void)n0;
+      const int buf = lt & 1;
+      const uint32_t acc = tmem_base + (uint32_t)(buf * 256);
+      mbar_wait(&tmem_empty[buf], (uint32_t)(((lt >> 1) & 1) ^ 1));   // epilogue drained this accumulator
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
         mbar_wait(&fullB[s], ph);
+        if (lane == 0) A32_TRACE(3, it);
         mbar_wait(&fullA[s], ph);
+        if (lane == 0) A32_TRACE(4, it);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
         const uint64_t dAh = make_sw128_desc(sa);
         const uint64_t dAl = make_sw128_desc(sa + a_bytes);
         const uint64_t dBh = make_sw128_desc(sa + 2 * a_bytes);
         const uint64_t dBl = make_sw128_desc(sa + 2 * a_bytes + b_bytes);
+        if (a32_elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          const uint64_t adv = (uint64_t)(k * 2);
-          umma_bf16(tmem_base, dAh + adv, dBh + adv, idesc, (i > 0 || k > 0) ? 1u : 0u);
-          umma_bf16(tmem_base, dAh + adv, dBl + adv, idesc, 1u);
-          umma_bf16(tmem_base, dAl + adv, dBh + adv, idesc, 1u);
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);
+            umma_bf16(acc, dAh + adv, dBh + adv, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(acc, dAh + adv, dBl + adv, idesc, 1u);
+            umma_bf16(acc, dAl + adv, dBh + adv, idesc, 1u);
+          }
+          umma_commit(&empty[s]);
+          if (i == nkb - 1) umma_commit(&tmem_full[buf]);
         }
-        umma_commit(&empty[s]);
+        __syncwarp();
+        if (lane == 0) A32_TRACE(5, it);
       }
-      umma_commit(tmem_full);
     }
-  } else {
-    // =============== A producers (main loop), then epilogue: 8 warps, 256 threads ===============
+  } else if (warp < 10) {
+    // =============== A producers: 8 warps, 256 threads ===============
     const int t = threadIdx.x - 64;  // 0..255
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles_total; tile += gridDim.x) {
+    A32_TILE_DECODE(tile)
+    (void)n0;
     const float* mv = p.mask ? p.mask + (long long)var * p.mask_var_stride : nullptr;
     if constexpr (MODE == 1) {
       // ---------------- fast row-major producer ----------------
@@ -158,14 +215,16 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
         }
       };
       if (nkb > 0) ld(0, xa, mAa, mBa);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % p.stages;
-        const uint32_t ph = (i / p.stages) & 1;
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
         uint8_t* Ah = smem + (size_t)s * stage_bytes + off0;
         uint8_t* Al = Ah + a_bytes;
         const bool odd = i & 1;
         if (i + 1 < nkb) { if (odd) ld(i + 1, xa, mAa, mBa); else ld(i + 1, xb, mAb, mBb); }
+        if (t == 0) A32_TRACE(0, it);
         mbar_wait(&empty[s], ph ^ 1);
+        if (t == 0) A32_TRACE(1, it);
         const float4 mA = odd ? mAb : mAa, mB = odd ? mBb : mBa;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -180,6 +239,7 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
+        if (t == 0) A32_TRACE(2, it);
       }
     } else if constexpr (MODE == 2) {
       // ---------------- fast transposed producer ----------------
@@ -228,14 +288,16 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
 #pragma unroll
         for (int g = 0; g < 4; ++g) { ma[sI][g] = 1.f; mb[sI][g] = 1.f; }
       if (nkb > 0) ld(0, xa, ma, selA_mask);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % p.stages;
-        const uint32_t ph = (i / p.stages) & 1;
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
         uint8_t* Ah = smem + (size_t)s * stage_bytes + off0;
         uint8_t* Al = Ah + a_bytes;
         const bool odd = i & 1;
         if (i + 1 < nkb) { if (odd) ld(i + 1, xa, ma, selA_mask); else ld(i + 1, xb, mb, selB_mask); }
+        if (t == 0) A32_TRACE(0, it);
         mbar_wait(&empty[s], ph ^ 1);
+        if (t == 0) A32_TRACE(1, it);
         const int sel = odd ? selB_mask : selA_mask;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -252,6 +314,7 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
+        if (t == 0) A32_TRACE(2, it);
       }
     } else {
     constexpr int NV = 8;            // float4 per thread per k-block (128 x 64 floats / 256 threads / 4)
@@ -315,9 +378,9 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
     };
     float4 va[NV], vb[NV];
     if (nkb > 0) load_tile(0, va);
-    for (int i = 0; i < nkb; ++i) {
-      const int s = i % p.stages;
-      const uint32_t ph = (i / p.stages) & 1;
+    for (int i = 0; i < nkb; ++i, ++it) {
+      const int s = it % p.stages;
+      const uint32_t ph = (it / p.stages) & 1;
       uint8_t* Ah = smem + (size_t)s * stage_bytes;
       uint8_t* Al = Ah + a_bytes;
       float4* cur = (i & 1) ? vb : va;
@@ -354,58 +417,79 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
     }
     }
-    // ---- epilogue: warps w and w+4 share TMEM lanes 32*(w%4)..+31 and split the columns
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    mbar_wait(tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int row = m0 + q * 32 + lane;
-    const int cbase = var * p.Nv + n0;     // first output column of this tile
-    const bool add_bias = p.bias != nullptr && blockIdx.z == 0;
-    for (int c0 = half * 32; c0 < BN; c0 += 64) {
-      uint32_t v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr)
-          : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < p.M && nkb > 0) {
-        float* crow = p.C + (size_t)row * p.ldc + cbase + c0;
-        const int ncol = min(32, min(BN - c0, p.Nv - (n0 + c0)));
+    }  // tile loop (producers)
+  } else {
+    // =============== epilogue: 4 warps; warp q owns TMEM lanes (= tile rows) 32q..32q+31 ===============
+    const int q = warp & 3;           // warps 10..13 -> 2, 3, 0, 1: any bijection onto the lane groups works
+    const int et = (int)threadIdx.x - 320;   // 0..127
+    const uint32_t r = (uint32_t)(q * 32 + lane);   // row inside the tile
+    int lt = 0, cc = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles_total; tile += gridDim.x, ++lt) {
+      A32_TILE_DECODE(tile)
+      (void)nkb;
+      const int buf = lt & 1;
+      mbar_wait(&tmem_full[buf], (uint32_t)((lt >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = m0 + (int)r;
+      const int cbase = var * p.Nv + n0;     // first output column of this tile
+      const bool add_bias = p.bias != nullptr && z_ == 0;
+      for (int c0 = 0; c0 < BN && n0 + c0 < p.Nv; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int ncol = min(32, p.Nv - (n0 + c0));
         const float* brow = p.bias ? p.bias + cbase + c0 : nullptr;
         if (p.use_atomic) {
-          for (int c = 0; c < ncol; ++c) {
-            float x = __uint_as_float(v[c]);
-            if (add_bias) x += brow[c];
-            atomicAdd(crow + c, x);
-          }
-        } else if (ncol == 32 && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0) &&
-                   (!add_bias || (reinterpret_cast<uintptr_t>(brow) & 15) == 0)) {
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            float4 o = make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
-            if (add_bias) {
-              const float4 bb = *reinterpret_cast<const float4*>(brow + c);
-              o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+          if (row < p.M) {
+            float* crow = p.C + (size_t)row * p.ldc + cbase + c0;
+            for (int c = 0; c < ncol; ++c) {
+              float x = __uint_as_float(v[c]);
+              if (add_bias) x += brow[c];
+              atomicAdd(crow + c, x);
             }
-            *reinterpret_cast<float4*>(crow + c) = o;
           }
         } else {
-          for (int c = 0; c < ncol; ++c) {
-            float x = __uint_as_float(v[c]);
-            if (add_bias) x += brow[c];
-            crow[c] = x;
+          // registers -> swizzled staging (conflict-free STS.128) -> one TMA tensor store per 32
+          // columns; rows >= M and columns >= Nv are clipped by the tensor map
+          uint8_t* stg = epi + (size_t)(cc & 1) * kEpiStage;
+          if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer's previous store has read it
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                   __uint_as_float(v[4 * j + 3]));
+            if (add_bias) {
+              if (4 * j < ncol) o.x += brow[4 * j];
+              if (4 * j + 1 < ncol) o.y += brow[4 * j + 1];
+              if (4 * j + 2 < ncol) o.z += brow[4 * j + 2];
+              if (4 * j + 3 < ncol) o.w += brow[4 * j + 3];
+            }
+            *reinterpret_cast<float4*>(stg + r * 128u + (((uint32_t)j ^ (r & 7u)) << 4)) = o;
           }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (et == 0) {
+            a32_tma_store_3d(&tmC, stg, n0 + c0, m0, var);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ++cc;
         }
       }
+      // this accumulator may be overwritten by the MMA warp (tile lt + 2)
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
     }
+    if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -416,6 +500,12 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
 }
 
 }  // namespace gr
+
+static long long* g_a32_trace = nullptr;
+extern "C" int gr_debug_a32_trace(long long* host_out, size_t n) {
+  if (!g_a32_trace) return -1;
+  return cudaMemcpy(host_out, g_a32_trace, n * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
 
 extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shift, const float* mask,
                                int rows_per_seq, int nvar, const void* b_hi, const void* b_lo, int ldb,
@@ -438,9 +528,10 @@ extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shif
   const int inner = transA ? M : K;
   p.aligned4 = ((lda % 4) == 0 && (inner % 4) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
                 (!mask || (reinterpret_cast<uintptr_t>(mask) & 15) == 0)) ? 1 : 0;
-  // tile width: as few equal tiles as possible, each <= 256 and a multiple of 16
+  // tile width: as few equal tiles as possible, each <= 256 and a multiple of 32 (the epilogue moves
+  // 32-column chunks)
   const int nt = (Nv + 255) / 256;
-  p.BN = (((Nv + nt - 1) / nt) + 15) / 16 * 16;
+  p.BN = (((Nv + nt - 1) / nt) + 31) / 32 * 32;
   p.ntile = (Nv + p.BN - 1) / p.BN;
   p.kb_total = (K + kBK - 1) / kBK;
   const int mt = (M + 127) / 128;
@@ -453,22 +544,41 @@ extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shif
   }
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
-  p.use_atomic = (splits > 1 || accumulate) ? 1 : 0;
-  if (splits > 1 && !accumulate) GR_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)nvar * Nv * 4, M, s));
+  // the TMA-store epilogue needs 16-byte aligned rows / variant blocks; otherwise fp32 atomics
+  const bool tma_ok = (ldc % 4) == 0 && (Nv % 4) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+  p.use_atomic = (splits > 1 || accumulate || !tma_ok) ? 1 : 0;
+  if (p.use_atomic && !accumulate) GR_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)nvar * Nv * 4, M, s));
+  p.trace = nullptr;
+  if (getenv("GR_A32_TRACE")) {
+    if (!g_a32_trace) GR_CUDA(cudaMalloc(&g_a32_trace, (size_t)160 * 64 * 8 * 8));
+    GR_CUDA(cudaMemsetAsync(g_a32_trace, 0, (size_t)160 * 64 * 8 * 8, s));
+    p.trace = g_a32_trace;
+  }
+  p.splits = splits;
+  p.tiles_n = p.ntile * nvar;
+  p.ntiles_total = (int)(tiles * splits);
   const size_t stage_bytes = 2 * ((size_t)128 * kBK * 2 + (size_t)p.BN * kBK * 2);
-  int stages = (int)((200 * 1024) / stage_bytes);
+  int stages = (int)((227 * 1024 - 1024 - 2 * kEpiStage - 256) / stage_bytes);
   if (stages > 4) stages = 4;
   if (stages < 2) return set_error(GR_EUNSUPPORTED, "gemm_a32: tile does not fit shared memory");
   p.stages = stages;
-  int tc = 32;
-  while (tc < p.BN) tc <<= 1;
-  p.tmem_cols = tc;
-  const size_t smem = 1024 + stages * stage_bytes + (3 * stages + 1) * 8 + 16;
-  CUtensorMap tBh, tBl;
+  p.tmem_cols = 512;   // two accumulators of <= 256 columns
+  const size_t smem = 1024 + stages * stage_bytes + 2 * kEpiStage + (3 * stages + 4) * 8 + 16;
+  CUtensorMap tBh, tBl, tC;
   int rc;
   if ((rc = make_map(&tBh, b_hi, (uint64_t)nvar * Nv, ldb, ldb, p.BN)) != GR_OK) return rc;
   if ((rc = make_map(&tBl, b_lo, (uint64_t)nvar * Nv, ldb, ldb, p.BN)) != GR_OK) return rc;
-  dim3 grid(p.ntile * nvar, mt, splits);
+  if (tma_ok) {
+    // (column within variant, row, variant): columns >= Nv and rows >= M are clipped on store
+    const cuuint64_t dims[3] = {(cuuint64_t)Nv, (cuuint64_t)M, (cuuint64_t)nvar};
+    const cuuint64_t strides[2] = {(cuuint64_t)ldc * 4, (cuuint64_t)Nv * 4};
+    const cuuint32_t box[3] = {32, 128, 1};
+    if ((rc = make_map_nd(&tC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, C, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) != GR_OK)
+      return rc;
+  } else {
+    tC = tBh;   // unused by the atomic epilogue
+  }
+  dim3 grid((unsigned)min((long long)sms, tiles * splits));
   int mode = 0;
   const char* force = getenv("GR_A32_MODE");
   if (!transA && p.aligned4 && (!mask || rows_per_seq >= 128)) mode = 1;
@@ -476,13 +586,13 @@ extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shif
   if (force && force[0] == '0') mode = 0;
   if (mode == 1) {
     GR_CUDA(cudaFuncSetAttribute(gemm_a32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_a32_kernel<1><<<grid, kA32Threads, smem, s>>>(tBh, tBl, p);
+    gemm_a32_kernel<1><<<grid, kA32Threads, smem, s>>>(tBh, tBl, tC, p);
   } else if (mode == 2) {
     GR_CUDA(cudaFuncSetAttribute(gemm_a32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_a32_kernel<2><<<grid, kA32Threads, smem, s>>>(tBh, tBl, p);
+    gemm_a32_kernel<2><<<grid, kA32Threads, smem, s>>>(tBh, tBl, tC, p);
   } else {
     GR_CUDA(cudaFuncSetAttribute(gemm_a32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_a32_kernel<0><<<grid, kA32Threads, smem, s>>>(tBh, tBl, p);
+    gemm_a32_kernel<0><<<grid, kA32Threads, smem, s>>>(tBh, tBl, tC, p);
   }
   GR_CHECK_LAUNCH("gemm_a32_kernel");
   return GR_OK;
