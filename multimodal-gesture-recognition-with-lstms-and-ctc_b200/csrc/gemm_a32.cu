@@ -41,7 +41,7 @@ struct A32Params {
   int splits, tiles_n, ntiles_total;   // tile t = ((m tile * tiles_n) + (variant, n tile)) * splits + k split
 };
 
-#define A32_TRACE(slot, it) do { if (p.trace && (it) < 64) p.trace[((size_t)blockIdx.x * 64 + (it)) * 8 + (slot)] = clock64(); } while (0)
+#define A32_TRACE(slot, it) do { if (p.trace && (it) < 64) p.trace[((size_t)blockIdx.x * 64 + (it)) * 16 + (slot)] = clock64(); } while (0)
 __device__ __forceinline__ bool a32_elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -58,11 +58,13 @@ __device__ __forceinline__ void split2(float v, uint32_t& hi, uint32_t& lo) {
   lo = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
 }
 
-// pack two floats into bf16x2 (hi) and the bf16x2 of their residuals (lo); element a in the low half
+// pack two floats into bf16x2 (hi) and the bf16x2 of their residuals (lo); element a in the low half.
+// hi is the TRUNCATED upper half (one PRMT for the pair, no conversion instruction), lo = a - hi is
+// exact in fp32 and rounded to nearest: |a - (hi + lo)| <= 2^-16 |a|, unbiased.
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  const float fa = __uint_as_float(hi << 16), fb = __uint_as_float(hi & 0xffff0000u);
+  const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+  hi = __byte_perm(ua, ub, 0x7632);
+  const float fa = __uint_as_float(ua & 0xffff0000u), fb = __uint_as_float(ub & 0xffff0000u);
   const __nv_bfloat162 l = __floats2bfloat162_rn(a - fa, b - fb);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
@@ -203,63 +205,76 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
       const float* mpB = mv ? mv + (size_t)min(seqA + 1, nseq - 1) * p.K + kq * 4 : nullptr;
       const uint32_t off0 = (uint32_t)rbase * 128u + ((((uint32_t)kq >> 1) ^ ((uint32_t)rbase & 7u)) << 4) + ((uint32_t)kq & 1u) * 8u;
       const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 xa[8], xb[8], mAa = one4, mBa = one4, mAb = one4, mBb = one4;
-      auto ld = [&](int i, float4* x, float4& mA, float4& mB) {
+      float4 xa[8], mAa = one4, mBa = one4;
+      // loads of k-block i: rows j0..j0+3 of this thread (and, with the second half, the masks)
+      auto ld = [&](int i, int j0, float4* x, float4& mA, float4& mB) {
         const int koff = (kb_begin + i) * kBK;
         const bool kv = koff + kq * 4 < p.K;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = (kv && rok[j]) ? __ldg(reinterpret_cast<const float4*>(ap[j] + koff)) : zero4;
-        if (mv) {
+        for (int j = 0; j < 4; ++j) x[j0 + j] = (kv && rok[j0 + j]) ? __ldg(reinterpret_cast<const float4*>(ap[j0 + j] + koff)) : zero4;
+        if (mv && j0 == 4) {
           mA = kv ? __ldg(reinterpret_cast<const float4*>(mpA + koff)) : zero4;
           mB = kv ? __ldg(reinterpret_cast<const float4*>(mpB + koff)) : zero4;
         }
       };
-      if (nkb > 0) ld(0, xa, mAa, mBa);
+      if (nkb > 0) { ld(0, 0, xa, mAa, mBa); ld(0, 4, xa, mAa, mBa); }
+      // one k-block: prefetch block i+1 into `nx`, convert block i from `cx`.  The two register
+      // buffers are selected STATICALLY (a runtime `odd ? xb : xa` select reads both operands and so
+      // waits for the prefetch it was meant to overlap).
+      // ONE register buffer: the loads of block i+1 are issued right after block i has been
+      // converted and are in flight while this thread waits for the next free stage (a second
+      // buffer does not fit 128 registers: ptxas then sinks the prefetch next to its use)
       for (int i = 0; i < nkb; ++i, ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (it / p.stages) & 1;
         uint8_t* Ah = smem + (size_t)s * stage_bytes + off0;
         uint8_t* Al = Ah + a_bytes;
-        const bool odd = i & 1;
-        if (i + 1 < nkb) { if (odd) ld(i + 1, xa, mAa, mBa); else ld(i + 1, xb, mAb, mBb); }
         if (t == 0) A32_TRACE(0, it);
         mbar_wait(&empty[s], ph ^ 1);
         if (t == 0) A32_TRACE(1, it);
-        const float4 mA = odd ? mAb : mAa, mB = odd ? mBb : mBa;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 x = odd ? xb[j] : xa[j];
-          const float4 mm = selB[j] ? mB : mA;
-          x.x *= mm.x; x.y *= mm.y; x.z *= mm.z; x.w *= mm.w;
-          uint32_t h01, l01, h23, l23;
-          split_pair(x.x, x.y, h01, l01);
-          split_pair(x.z, x.w, h23, l23);
-          *reinterpret_cast<uint2*>(Ah + j * 2048) = make_uint2(h01, h23);
-          *reinterpret_cast<uint2*>(Al + j * 2048) = make_uint2(l01, l23);
+        for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+          for (int j = 4 * hf; j < 4 * hf + 4; ++j) {
+            float4 x = xa[j];
+            const float4 mm = selB[j] ? mBa : mAa;
+            x.x *= mm.x; x.y *= mm.y; x.z *= mm.z; x.w *= mm.w;
+            uint32_t h01, l01, h23, l23;
+            split_pair(x.x, x.y, h01, l01);
+            split_pair(x.z, x.w, h23, l23);
+            *reinterpret_cast<uint2*>(Ah + j * 2048) = make_uint2(h01, h23);
+            *reinterpret_cast<uint2*>(Al + j * 2048) = make_uint2(l01, l23);
+          }
+          if (t == 0) A32_TRACE(8 + 2 * hf, it);
+          // the registers of this half are free: its loads of block i+1 overlap the other half
+          if (i + 1 < nkb) ld(i + 1, 4 * hf, xa, mAa, mBa);
+          if (t == 0) A32_TRACE(9 + 2 * hf, it);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (t == 0) A32_TRACE(12, it);
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
         if (t == 0) A32_TRACE(2, it);
       }
     } else if constexpr (MODE == 2) {
       // ---------------- fast transposed producer ----------------
-      // warp w <-> k rows 8w..8w+7 of the k-block (one 16-byte chunk per output row);
-      // lane <-> m: rows lane + 32 g.  Loads are 128 B coalesced per k row; stores are STS.128.
+      // warp w <-> tile rows (m) 16w..16w+15; lane = kc*4 + mq: k rows 8kc..8kc+7 of the k-block (one
+      // 16-byte chunk of each output row) x the float4 of m = 16w + 4mq..+3.  Loads are 128-bit
+      // (8 per thread per k-block instead of 32 scalar ones, which capped the SM's requests in
+      // flight); stores are STS.128 with 2-way bank conflicts.
       const int w = t >> 5, ln = t & 31;
+      const int kc = ln >> 2, mq = ln & 3;
       const int T_ = p.rows_per_seq;
       const int nseq = (p.K + T_ - 1) / T_;
-      bool mok[4];
-      const float* ap[4];
-#pragma unroll
-      for (int g = 0; g < 4; ++g) { const int m = m0 + ln + 32 * g; mok[g] = m < p.M; ap[g] = p.A + (mok[g] ? m : 0); }
-      const uint32_t off0 = (uint32_t)ln * 128u + (((uint32_t)w ^ ((uint32_t)ln & 7u)) << 4);
-      float xa[4][8], xb[4][8], ma[2][4], mb[2][4];
-      int selA_mask = 0, selB_mask = 0;   // bit kk set: row kk belongs to the second sequence of the block
-      auto ld = [&](int i, float (*x)[8], float (*mk)[4], int& sel) {
-        const int kbase = (kb_begin + i) * kBK + 8 * w;
+      const int rloc = 16 * w + 4 * mq;              // first tile row of this thread
+      const bool mok = m0 + rloc < p.M;              // M % 4 == 0: the float4 is all-in or all-out
+      const float* ap = p.A + (mok ? m0 + rloc : 0);
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f), one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+      float4 xa[8], ma[2];
+      int selA_mask = 0;   // bit kk set: row kk belongs to the second sequence of the block
+      auto ld = [&](int i, float4* x, float4* mk, int& sel) {
+        const int kbase = (kb_begin + i) * kBK + 8 * kc;
         const int seq0 = ((kb_begin + i) * kBK) / T_;
         sel = 0;
-#pragma unroll
         const int sqb = kbase / T_;
         const int ttb = kbase - sqb * T_;
 #pragma unroll
@@ -271,47 +286,46 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
           const bool ok = kg < p.K && tt >= 0 && tt < T_;
           if (sq != seq0) sel |= 1 << kk;
           const size_t roff = (size_t)(ok ? kg + p.row_shift : 0) * p.lda;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) x[g][kk] = (ok && mok[g]) ? __ldg(ap[g] + roff) : 0.f;
+          x[kk] = (ok && mok) ? __ldg(reinterpret_cast<const float4*>(ap + roff)) : zero4;
         }
         if (mv) {
 #pragma unroll
-          for (int sI = 0; sI < 2; ++sI) {
-            const float* mp = mv + (size_t)min(seq0 + sI, nseq - 1) * p.M + m0 + ln;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) mk[sI][g] = mok[g] ? __ldg(mp + 32 * g) : 0.f;
-          }
+          for (int sI = 0; sI < 2; ++sI)
+            mk[sI] = mok ? __ldg(reinterpret_cast<const float4*>(mv + (size_t)min(seq0 + sI, nseq - 1) * p.M + m0 + rloc)) : zero4;
         }
       };
-#pragma unroll
-      for (int sI = 0; sI < 2; ++sI)
-#pragma unroll
-        for (int g = 0; g < 4; ++g) { ma[sI][g] = 1.f; mb[sI][g] = 1.f; }
+      ma[0] = ma[1] = one4;
       if (nkb > 0) ld(0, xa, ma, selA_mask);
       for (int i = 0; i < nkb; ++i, ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (it / p.stages) & 1;
-        uint8_t* Ah = smem + (size_t)s * stage_bytes + off0;
+        uint8_t* Ah = smem + (size_t)s * stage_bytes;
         uint8_t* Al = Ah + a_bytes;
-        const bool odd = i & 1;
-        if (i + 1 < nkb) { if (odd) ld(i + 1, xa, ma, selA_mask); else ld(i + 1, xb, mb, selB_mask); }
         if (t == 0) A32_TRACE(0, it);
         mbar_wait(&empty[s], ph ^ 1);
         if (t == 0) A32_TRACE(1, it);
-        const int sel = odd ? selB_mask : selA_mask;
+        const float4 m_0 = ma[0], m_1 = ma[1];
+        const int sel = selA_mask;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const float m_0 = odd ? mb[0][g] : ma[0][g], m_1 = odd ? mb[1][g] : ma[1][g];
+          const float mg0 = g == 0 ? m_0.x : g == 1 ? m_0.y : g == 2 ? m_0.z : m_0.w;
+          const float mg1 = g == 0 ? m_1.x : g == 1 ? m_1.y : g == 2 ? m_1.z : m_1.w;
           uint32_t hh[4], ll[4];
 #pragma unroll
           for (int kk = 0; kk < 8; kk += 2) {
-            const float a0 = (odd ? xb[g][kk] : xa[g][kk]) * (((sel >> kk) & 1) ? m_1 : m_0);
-            const float a1 = (odd ? xb[g][kk + 1] : xa[g][kk + 1]) * (((sel >> (kk + 1)) & 1) ? m_1 : m_0);
+            const float4 v0 = xa[kk], v1 = xa[kk + 1];
+            const float e0 = g == 0 ? v0.x : g == 1 ? v0.y : g == 2 ? v0.z : v0.w;
+            const float e1 = g == 0 ? v1.x : g == 1 ? v1.y : g == 2 ? v1.z : v1.w;
+            const float a0 = e0 * (((sel >> kk) & 1) ? mg1 : mg0);
+            const float a1 = e1 * (((sel >> (kk + 1)) & 1) ? mg1 : mg0);
             split_pair(a0, a1, hh[kk >> 1], ll[kk >> 1]);
           }
-          *reinterpret_cast<uint4*>(Ah + g * 4096) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-          *reinterpret_cast<uint4*>(Al + g * 4096) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+          const uint32_t r = (uint32_t)(rloc + g);
+          const uint32_t off = r * 128u + (((uint32_t)kc ^ (r & 7u)) << 4);
+          *reinterpret_cast<uint4*>(Ah + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+          *reinterpret_cast<uint4*>(Al + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
         }
+        if (i + 1 < nkb) ld(i + 1, xa, ma, selA_mask);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
         if (t == 0) A32_TRACE(2, it);
@@ -550,8 +564,8 @@ extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shif
   if (p.use_atomic && !accumulate) GR_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)nvar * Nv * 4, M, s));
   p.trace = nullptr;
   if (getenv("GR_A32_TRACE")) {
-    if (!g_a32_trace) GR_CUDA(cudaMalloc(&g_a32_trace, (size_t)160 * 64 * 8 * 8));
-    GR_CUDA(cudaMemsetAsync(g_a32_trace, 0, (size_t)160 * 64 * 8 * 8, s));
+    if (!g_a32_trace) GR_CUDA(cudaMalloc(&g_a32_trace, (size_t)160 * 64 * 16 * 8));
+    GR_CUDA(cudaMemsetAsync(g_a32_trace, 0, (size_t)160 * 64 * 16 * 8, s));
     p.trace = g_a32_trace;
   }
   p.splits = splits;
@@ -582,7 +596,7 @@ extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shif
   int mode = 0;
   const char* force = getenv("GR_A32_MODE");
   if (!transA && p.aligned4 && (!mask || rows_per_seq >= 128)) mode = 1;
-  if (transA && rows_per_seq >= 64) mode = 2;
+  if (transA && p.aligned4 && rows_per_seq >= 64) mode = 2;
   if (force && force[0] == '0') mode = 0;
   if (mode == 1) {
     GR_CUDA(cudaFuncSetAttribute(gemm_a32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -12,6 +12,11 @@ namespace gr {
 
 __device__ __forceinline__ float hsig_s(float v) { return fminf(fmaxf(0.2f * v + 0.5f, 0.f), 1.f); }
 __device__ __forceinline__ float dhsig_s(float s) { return (s > 0.f && s < 1.f) ? 0.2f : 0.f; }
+// tanh(x) = 1 - 2/(1 + e^{2x}) on MUFU ex2 + fast division: absolute error ~1e-7 (as lstm_tc.cu)
+__device__ __forceinline__ float tanh_s(float x) {
+  const float e = ex2_approx(x * 2.8853900817779268f);
+  return 1.0f - __fdividef(2.0f, 1.0f + e);
+}
 
 struct SmallParams {
   float* gates;        // (B,T,8H)  fwd: P in / gates out (if save);  bwd: gates in / dP out
@@ -22,10 +27,12 @@ struct SmallParams {
   int B, T, H, BS, save;
 };
 
-template <int HP>
+// BS (sequences per CTA) is a template parameter: with a runtime bound the matvec loop kept a branch
+// per (k, sequence) and every LDS -> 4 dependent FMAs chain ran serially (6.8 us / step at H = 100).
+template <int HP, int BS>
 __global__ void __launch_bounds__(4 * HP, 1) lstm_small_fwd_kernel(SmallParams p) {
   extern __shared__ __align__(16) float sm[];
-  const int H = p.H, T = p.T, BS = p.BS, H4 = 4 * H;
+  const int H = p.H, T = p.T, H4 = 4 * H;
   float* hs = sm;                 // BS * HP   (h_{t-1}, zero padded to HP)
   float* zs = hs + BS * HP;       // BS * H4
   const int nbg = (p.B + BS - 1) / BS;
@@ -43,43 +50,49 @@ __global__ void __launch_bounds__(4 * HP, 1) lstm_small_fwd_kernel(SmallParams p
   float c_state = 0.f;
   const size_t G8 = (size_t)8 * H, Y2 = (size_t)2 * H;
   __syncthreads();
+  // pre-activations of step 0; step s+1's are prefetched while step s computes
+  float pre[4] = {0.f, 0.f, 0.f, 0.f};
+  if (eact) {
+    const float* g0 = p.gates + ((size_t)(b0 + eb) * T + (dir == 0 ? 0 : T - 1)) * G8 + (size_t)dir * H4 + ej;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) pre[g] = g0[(size_t)g * H];
+  }
   for (int s = 0; s < T; ++s) {
     const int t = dir == 0 ? s : T - 1 - s;
-    float pre[4] = {0.f, 0.f, 0.f, 0.f};
-    float* grow = nullptr;
-    if (eact) {
-      grow = p.gates + ((size_t)(b0 + eb) * T + t) * G8 + (size_t)dir * H4 + ej;
+    float* grow = eact ? p.gates + ((size_t)(b0 + eb) * T + t) * G8 + (size_t)dir * H4 + ej : nullptr;
+    float nxt[4] = {0.f, 0.f, 0.f, 0.f};
+    if (eact && s + 1 < T) {
+      const float* gn = grow + (dir == 0 ? (ptrdiff_t)G8 : -(ptrdiff_t)G8);
 #pragma unroll
-      for (int g = 0; g < 4; ++g) pre[g] = grow[(size_t)g * H];
+      for (int g = 0; g < 4; ++g) nxt[g] = gn[(size_t)g * H];
     }
     if (s > 0 && n < H4) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      float acc[BS][2];
+#pragma unroll
+      for (int b = 0; b < BS; ++b) acc[b][0] = acc[b][1] = 0.f;
 #pragma unroll
       for (int k = 0; k < HP; k += 4) {
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          if (b < BS) {
-            const float4 h = *reinterpret_cast<const float4*>(hs + b * HP + k);
-            acc[b] = fmaf(h.x, ureg[k], acc[b]);
-            acc[b] = fmaf(h.y, ureg[k + 1], acc[b]);
-            acc[b] = fmaf(h.z, ureg[k + 2], acc[b]);
-            acc[b] = fmaf(h.w, ureg[k + 3], acc[b]);
-          }
+        for (int b = 0; b < BS; ++b) {
+          const float4 h = *reinterpret_cast<const float4*>(hs + b * HP + k);
+          acc[b][0] = fmaf(h.x, ureg[k], acc[b][0]);
+          acc[b][1] = fmaf(h.y, ureg[k + 1], acc[b][1]);
+          acc[b][0] = fmaf(h.z, ureg[k + 2], acc[b][0]);
+          acc[b][1] = fmaf(h.w, ureg[k + 3], acc[b][1]);
         }
       }
 #pragma unroll
-      for (int b = 0; b < 4; ++b)
-        if (b < BS) zs[b * H4 + n] = acc[b];
+      for (int b = 0; b < BS; ++b) zs[b * H4 + n] = acc[b][0] + acc[b][1];
     }
     __syncthreads();
     if (eact) {
       float z[4];
 #pragma unroll
       for (int g = 0; g < 4; ++g) z[g] = pre[g] + (s > 0 ? zs[eb * H4 + g * H + ej] : 0.f);
-      const float gi = hsig_s(z[0]), gf = hsig_s(z[1]), gg = tanhf(z[2]), go = hsig_s(z[3]);
+      const float gi = hsig_s(z[0]), gf = hsig_s(z[1]), gg = tanh_s(z[2]), go = hsig_s(z[3]);
       const float c = gf * c_state + gi * gg;
       c_state = c;
-      const float h = go * tanhf(c);
+      const float h = go * tanh_s(c);
       hs[eb * HP + ej] = h;
       p.y[((size_t)(b0 + eb) * T + t) * Y2 + (size_t)dir * H + ej] = h;
       if (p.save) {
@@ -87,14 +100,16 @@ __global__ void __launch_bounds__(4 * HP, 1) lstm_small_fwd_kernel(SmallParams p
         p.cell[((size_t)(b0 + eb) * T + t) * Y2 + (size_t)dir * H + ej] = c;
       }
     }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) pre[g] = nxt[g];
     __syncthreads();
   }
 }
 
-template <int HP>
+template <int HP, int BS>
 __global__ void __launch_bounds__(4 * HP, 1) lstm_small_bwd_kernel(SmallParams p) {
   extern __shared__ __align__(16) float sm[];
-  const int H = p.H, T = p.T, BS = p.BS, H4 = 4 * H;
+  const int H = p.H, T = p.T, H4 = 4 * H;
   const int QS = 4 * HP;            // padded stride of one sequence's dG row: 4 quarters of HP
   float* dgs = sm;                  // BS * QS   dG_{next}, quarter q at [q*HP, q*HP+H), zero padded
   float* part = dgs + BS * QS;      // 4 * BS * H partial sums
@@ -129,30 +144,29 @@ __global__ void __launch_bounds__(4 * HP, 1) lstm_small_bwd_kernel(SmallParams p
       dyv = p.dy[row * Y2 + (size_t)dir * H + ej];
     }
     if (sp > 0 && mact) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      float acc[BS][2];
+#pragma unroll
+      for (int b = 0; b < BS; ++b) acc[b][0] = acc[b][1] = 0.f;
 #pragma unroll
       for (int i = 0; i < HP; i += 4) {
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          if (b < BS) {
-            const float4 g4 = *reinterpret_cast<const float4*>(dgs + b * QS + q * HP + i);
-            acc[b] = fmaf(g4.x, ureg[i], acc[b]);
-            acc[b] = fmaf(g4.y, ureg[i + 1], acc[b]);
-            acc[b] = fmaf(g4.z, ureg[i + 2], acc[b]);
-            acc[b] = fmaf(g4.w, ureg[i + 3], acc[b]);
-          }
+        for (int b = 0; b < BS; ++b) {
+          const float4 g4 = *reinterpret_cast<const float4*>(dgs + b * QS + q * HP + i);
+          acc[b][0] = fmaf(g4.x, ureg[i], acc[b][0]);
+          acc[b][1] = fmaf(g4.y, ureg[i + 1], acc[b][1]);
+          acc[b][0] = fmaf(g4.z, ureg[i + 2], acc[b][0]);
+          acc[b][1] = fmaf(g4.w, ureg[i + 3], acc[b][1]);
         }
       }
 #pragma unroll
-      for (int b = 0; b < 4; ++b)
-        if (b < BS) part[(q * BS + b) * H + j] = acc[b];
+      for (int b = 0; b < BS; ++b) part[(q * BS + b) * H + j] = acc[b][0] + acc[b][1];
     }
     __syncthreads();
     if (eact) {
       float dh = dyv;
       if (sp > 0) dh += (part[(0 * BS + eb) * H + ej] + part[(1 * BS + eb) * H + ej]) +
                         (part[(2 * BS + eb) * H + ej] + part[(3 * BS + eb) * H + ej]);
-      const float tc = tanhf(c);
+      const float tc = tanh_s(c);
       const float dc = dc_carry + dh * go * (1.f - tc * tc);
       const float d_o = dh * tc * dhsig_s(go);
       const float d_i = dc * gg * dhsig_s(gi);
@@ -171,25 +185,32 @@ bool lstm_small_supported(int H) { return H % 4 == 0 && H >= 4 && H <= 104; }
 
 static int small_bs(int B) {
   const int per_dir = max(1, num_sms() / 2);
-  int bs = (B + per_dir - 1) / per_dir;
-  return bs < 1 ? 1 : (bs > 4 ? 4 : bs);
+  const int bs = (B + per_dir - 1) / per_dir;
+  return bs <= 1 ? 1 : (bs <= 2 ? 2 : 4);
 }
 
-template <int HP>
+template <int HP, int BS>
 static int small_launch(bool bwd, SmallParams& p, cudaStream_t s) {
-  const int nbg = (p.B + p.BS - 1) / p.BS;
+  const int nbg = (p.B + BS - 1) / BS;
   const int threads = ((4 * p.H + 31) / 32) * 32;
   if (!bwd) {
-    const size_t smem = sizeof(float) * ((size_t)p.BS * HP + (size_t)p.BS * 4 * p.H);
-    GR_CUDA(cudaFuncSetAttribute(lstm_small_fwd_kernel<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lstm_small_fwd_kernel<HP><<<2 * nbg, threads, smem, s>>>(p);
+    const size_t smem = sizeof(float) * ((size_t)BS * HP + (size_t)BS * 4 * p.H);
+    GR_CUDA(cudaFuncSetAttribute(lstm_small_fwd_kernel<HP, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lstm_small_fwd_kernel<HP, BS><<<2 * nbg, threads, smem, s>>>(p);
   } else {
-    const size_t smem = sizeof(float) * ((size_t)p.BS * 4 * HP + (size_t)4 * p.BS * p.H);
-    GR_CUDA(cudaFuncSetAttribute(lstm_small_bwd_kernel<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lstm_small_bwd_kernel<HP><<<2 * nbg, threads, smem, s>>>(p);
+    const size_t smem = sizeof(float) * ((size_t)BS * 4 * HP + (size_t)4 * BS * p.H);
+    GR_CUDA(cudaFuncSetAttribute(lstm_small_bwd_kernel<HP, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lstm_small_bwd_kernel<HP, BS><<<2 * nbg, threads, smem, s>>>(p);
   }
   GR_CHECK_LAUNCH("lstm_small_kernel");
   return GR_OK;
+}
+
+template <int HP>
+static int small_launch_bs(bool bwd, SmallParams& p, cudaStream_t s) {
+  if (p.BS == 1) return small_launch<HP, 1>(bwd, p, s);
+  if (p.BS == 2) return small_launch<HP, 2>(bwd, p, s);
+  return small_launch<HP, 4>(bwd, p, s);
 }
 
 int lstm_small_run(bool bwd, float* gates, const float* U, int B, int T, int H, float* y, float* cell,
@@ -199,9 +220,9 @@ int lstm_small_run(bool bwd, float* gates, const float* U, int B, int T, int H, 
   p.BS = small_bs(B);
   p.save = (!bwd && cell != nullptr) ? 1 : 0;
   // B > 4 * (SMs/2) sequences per direction are covered by more CTAs than SMs (several waves)
-  if (H <= 32) return small_launch<32>(bwd, p, s);
-  if (H <= 64) return small_launch<64>(bwd, p, s);
-  return small_launch<104>(bwd, p, s);
+  if (H <= 32) return small_launch_bs<32>(bwd, p, s);
+  if (H <= 64) return small_launch_bs<64>(bwd, p, s);
+  return small_launch_bs<104>(bwd, p, s);
 }
 
 }  // namespace gr

@@ -11,6 +11,8 @@ All regularisers are explicit arguments (inject them for parity, or draw them wi
 `sample_regularisers`, on-device Philox) because K.set_learning_phase(1) keeps them active in
 training AND in the frozen towers (speech:40, multimodal.py:66).
 """
+import os
+
 import torch
 from torch import nn
 
@@ -124,6 +126,8 @@ class FusionNet(nn.Module):
         with torch.no_grad():
             # the two towers are independent until the concat (multimodal.py:109-118,155): run them on
             # two streams -- their recurrences (64 + 40 persistent CTAs) and GEMMs overlap on the 148 SMs
+            if os.environ.get("GR_TOWER_STREAMS", "1") == "0":
+                return ops.concat2(self.speech.tower(xa, reg.get("sp")), self.skeletal.tower(xs, reg.get("sk")))
             cur = torch.cuda.current_stream()
             if self._streams is None:
                 self._streams = (torch.cuda.Stream(), torch.cuda.Stream())

@@ -5,7 +5,7 @@ import torch
 from mgr_b200 import ops
 dev = torch.device("cuda:0")
 T = int(os.environ.get("T", "1000"))
-shapes = [(256, 500), (256, 300), (128, 500), (32, 500), (32, 300)]
+shapes = [tuple(int(v) for v in x.split("x")) for x in os.environ.get("SHAPES", "256x500,256x300,128x500,32x500,32x300").split(",")]
 for mode in ("bf16x3",):
     for (B, H) in shapes:
         gates = torch.randn(B * T, 8 * H, device=dev) * 0.5

@@ -26,14 +26,15 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); run(); e1.record(); torch.cuda.synchronize()
 print(what, "ms", e0.elapsed_time(e1))
 lib = _lib.load()
-n = 160 * 64 * 8
+n = 160 * 64 * 16
 buf = (ctypes.c_longlong * n)()
 assert lib.gr_debug_a32_trace(buf, ctypes.c_size_t(n)) == 0
-tr = np.frombuffer(buf, dtype=np.int64).reshape(160, 64, 8)
+tr = np.frombuffer(buf, dtype=np.int64).reshape(160, 64, 16)
 tr = tr[:148]
-names = ["prod: next loads issued", "prod: stage empty", "prod: stored+arrived", "mma: fullB", "mma: fullA", "mma: issued+commit", "tmaB: stage empty(issue)"]
+names = ["prod: iteration start", "prod: stage empty", "prod: stored+arrived", "mma: fullB", "mma: fullA", "mma: issued+commit", "tmaB: stage empty(issue)", "-",
+         "prod: half0 converted", "prod: half0 next loads issued", "prod: half1 converted", "prod: half1 next loads issued", "prod: fence done"]
 base = tr[:, 20:60, 0:1]
-rel = tr[:, 20:60, :7] - base
+rel = tr[:, 20:60, :13] - base
 for i, nme in enumerate(names):
     print("  %-26s med %7d" % (nme, np.median(rel[:, :, i])))
 per = np.median(np.diff(tr[:, 20:60, 2], axis=1))
