@@ -17,6 +17,7 @@
 //             publish h_t (bf16 hi/lo) to the exchange buffer, arrive on the step barrier, then
 //             stage y_t (+ gates, c when training) in shared memory
 //   warp 10   all bulk global traffic as TMA tensor copies: P_{t+1} load, y / gates / c stores.
+//   warp 11   second tcgen05.mma issuer (odd K chunks, second accumulator set).
 // Nothing but the 16 KB h publish and the barrier counter goes through the LSU: per-thread-row
 // global accesses (32 lines per warp instruction) used to occupy the LSU for ~5000 cycles per step
 // and sat in front of the barrier's release fence and poll (profiles/r01_lstm_tc_trace.txt).
@@ -34,7 +35,8 @@ namespace gr {
 static constexpr int kTcThreads = 384;   // TMA warp, MMA warp A, 8 epilogue warps, IO warp, MMA warp B
 static constexpr int kUnits = 16;        // hidden units per CTA
 static constexpr int kEU = 8;            // units per epilogue thread
-static constexpr int kMaxStages = 4;
+static constexpr int kEpiThreads = 256;   // (16 epilogue warps x 4 units were measured slower: MUFU-bound math, 8-byte publishes)
+static constexpr int kMaxStages = 5;     // ring stages incl. the P / gates tile, which serves as the last one
 static constexpr uint32_t kTile = 16384; // 128 rows x 128 B
 static constexpr uint32_t kStageBytes = 2 * kTile;
 static constexpr uint32_t kIoBytes = 32768;  // P / gates tile: [4 gates][128 rows][16 units] fp32
@@ -103,7 +105,11 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmUh, const __grid_consta
   uint64_t* p_full = tmem_full + 1;        // P_t tile landed
   uint64_t* stage_ready = p_full + 1;      // 256 epilogue threads staged step t's outputs
   uint64_t* out_done = stage_ready + 1;    // step t's TMA stores have read their staging
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(out_done + 1);
+  uint64_t* p_consumed = out_done + 1;     // 256 epilogue threads hold P_t in registers: the tile may carry h
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(p_consumed + 1);
+  // The P / gates tile is idle from the moment the epilogue has P_t in registers until the step's
+  // MMAs are done, so during the MMA phase it is ring stage NST (the stages are contiguous).
+  const int NSTT = NST + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ug = blockIdx.x % p.UGn;
@@ -124,8 +130,9 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmUh, const __grid_consta
     mbar_init(ufull, 1);
     mbar_init(tmem_full, 2);
     mbar_init(p_full, 1);
-    mbar_init(stage_ready, 256);
+    mbar_init(stage_ready, kEpiThreads);
     mbar_init(out_done, 1);
+    mbar_init(p_consumed, kEpiThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -153,8 +160,9 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmUh, const __grid_consta
     }
     __syncwarp();
     // ---- per step: stream h_{t-1} of this batch tile
-    int it = 0;
     for (int s = 1; s < T; ++s) {
+      // step barrier: one monotonic counter per (direction, batch tile).  (Per-CTA flags in one line
+      // polled warp-wide were tried: 32 writers + 32x32 pollers on one L2 line took 2.4x longer.)
       const unsigned target = (unsigned)s * p.UGn;
       unsigned v;
       do {
@@ -162,12 +170,14 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmUh, const __grid_consta
       } while (v < target);
       asm volatile("fence.proxy.async;" ::: "memory");
       if (lane == 0) TC_TRACE(0, s);
-      mbar_wait(out_done, (uint32_t)((s - 1) & 1));   // the last ring stage doubled as y/c staging
+      mbar_wait(out_done, (uint32_t)((s - 1) & 1));   // ring stage NST-1 doubled as y/c staging
       const int row = (dir * 2 + ((s + 1) & 1)) * p.Bpad + bt * 128;
-      for (int c = 0; c < nch; ++c, ++it) {
-        const int st = it % NST;
-        const uint32_t ph = (it / NST) & 1;
-        mbar_wait(&empty[st], ph ^ 1);
+      for (int c = 0; c < nch; ++c) {
+        // chunk c -> stage c % NSTT (restarting every step); its use index gives the phase
+        const int st = c % NSTT;
+        const uint32_t use = (uint32_t)(s - 1) * (uint32_t)((nch - st + NSTT - 1) / NSTT) + (uint32_t)(c / NSTT);
+        mbar_wait(&empty[st], (use & 1) ^ 1);
+        if (st == NST) mbar_wait(p_consumed, (uint32_t)(s & 1));
         if (elect_one()) {
           if (p.dbg & 1) {
             mbar_arrive(&full[st]);
@@ -190,11 +200,10 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmUh, const __grid_consta
     constexpr uint32_t idesc128 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     constexpr uint32_t idesc64 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     mbar_wait(ufull, 0);
-    int it = 0;
     for (int s = 1; s < T; ++s) {
-      for (int c = 0; c < nch; ++c, ++it) {
-        const int st = it % NST;
-        const uint32_t ph = (it / NST) & 1;
+      for (int c = 0; c < nch; ++c) {
+        const int st = c % NSTT;
+        const uint32_t ph = ((uint32_t)(s - 1) * (uint32_t)((nch - st + NSTT - 1) / NSTT) + (uint32_t)(c / NSTT)) & 1;
         // both warps observe every phase of every stage in order (a parity wait may lag the barrier
         // by at most one phase), the other warp's chunks are then skipped
         mbar_wait(&full[st], ph);
@@ -250,6 +259,7 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmUh, const __grid_consta
         pre[g][0] = a.x; pre[g][1] = a.y; pre[g][2] = a.z; pre[g][3] = a.w;
         pre[g][4] = b.x; pre[g][5] = b.y; pre[g][6] = b.z; pre[g][7] = b.w;
       }
+      mbar_arrive(p_consumed);
       if (s > 0) {
         mbar_wait(tmem_full, (uint32_t)((s - 1) & 1));
         if (threadIdx.x == 64) TC_TRACE(4, s);
@@ -390,6 +400,7 @@ static TcLayout tc_layout(int B, int H) {
   const long budget = 227 * 1024 - 1024 - 256 - (long)L.nch * kTile - kIoBytes;
   L.nstages = (int)(budget / (long)kStageBytes);
   if (L.nstages > kMaxStages) L.nstages = kMaxStages;
+  if (L.nstages > kMaxStages - 1) L.nstages = kMaxStages - 1;
   L.smem = 1024 + (size_t)L.nch * kTile + (size_t)(L.nstages > 0 ? L.nstages : 0) * kStageBytes + kIoBytes + 256;
   size_t o = 1024;
   L.off_hx = o; o += (size_t)2 * L.nch * 4 * L.Bpad * 128;   // (chunk, part) slabs of (dir, parity, row) x 128 B
@@ -408,7 +419,7 @@ bool lstm_tc_supported(int B, int H) {
   if (H % 4 != 0 || H < 32) return false;
   TcLayout L = tc_layout(B, H);
   if (2 * L.NBT * L.UGn > num_sms()) return false;
-  return L.nstages >= 2;
+  return L.nstages >= 1;
 }
 
 // (units, batch rows, time, variant) view of a (B, T, nvar*H) fp32 tensor; box = 16 x 128 x 1 x nbox
