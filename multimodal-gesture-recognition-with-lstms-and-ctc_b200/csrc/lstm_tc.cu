@@ -110,6 +110,9 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmUh, const __grid_consta
   // The P / gates tile is idle from the moment the epilogue has P_t in registers until the step's
   // MMAs are done, so during the MMA phase it is ring stage NST (the stages are contiguous).
   const int NSTT = NST + 1;
+  // chunk c -> ring stage c % NSTT, its rank among the step's uses of that stage, and the stage's uses
+  // per step: tabulated once (runtime divisions sat on the TMA / MMA issue paths)
+  __shared__ int tab_st[16], tab_m[16], tab_u[16];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ug = blockIdx.x % p.UGn;
@@ -133,6 +136,10 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmUh, const __grid_consta
     mbar_init(stage_ready, kEpiThreads);
     mbar_init(out_done, 1);
     mbar_init(p_consumed, kEpiThreads);
+    for (int c = 0; c < 16; ++c) {
+      const int st = c % NSTT;
+      tab_st[c] = st; tab_m[c] = c / NSTT; tab_u[c] = (nch - st + NSTT - 1) / NSTT;
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -174,8 +181,8 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmUh, const __grid_consta
       const int row = (dir * 2 + ((s + 1) & 1)) * p.Bpad + bt * 128;
       for (int c = 0; c < nch; ++c) {
         // chunk c -> stage c % NSTT (restarting every step); its use index gives the phase
-        const int st = c % NSTT;
-        const uint32_t use = (uint32_t)(s - 1) * (uint32_t)((nch - st + NSTT - 1) / NSTT) + (uint32_t)(c / NSTT);
+        const int st = tab_st[c];
+        const uint32_t use = (uint32_t)(s - 1) * (uint32_t)tab_u[c] + (uint32_t)tab_m[c];
         mbar_wait(&empty[st], (use & 1) ^ 1);
         if (st == NST) mbar_wait(p_consumed, (uint32_t)(s & 1));
         if (elect_one()) {
@@ -202,8 +209,8 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmUh, const __grid_consta
     mbar_wait(ufull, 0);
     for (int s = 1; s < T; ++s) {
       for (int c = 0; c < nch; ++c) {
-        const int st = c % NSTT;
-        const uint32_t ph = ((uint32_t)(s - 1) * (uint32_t)((nch - st + NSTT - 1) / NSTT) + (uint32_t)(c / NSTT)) & 1;
+        const int st = tab_st[c];
+        const uint32_t ph = ((uint32_t)(s - 1) * (uint32_t)tab_u[c] + (uint32_t)tab_m[c]) & 1;
         // both warps observe every phase of every stage in order (a parity wait may lag the barrier
         // by at most one phase), the other warp's chunks are then skipped
         mbar_wait(&full[st], ph);
@@ -419,7 +426,7 @@ bool lstm_tc_supported(int B, int H) {
   if (H % 4 != 0 || H < 32) return false;
   TcLayout L = tc_layout(B, H);
   if (2 * L.NBT * L.UGn > num_sms()) return false;
-  return L.nstages >= 1;
+  return L.nstages >= 1 && L.nch <= 16;
 }
 
 // (units, batch rows, time, variant) view of a (B, T, nvar*H) fp32 tensor; box = 16 x 128 x 1 x nbox

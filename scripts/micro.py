@@ -15,7 +15,7 @@ if what == "ctc":
     for _ in range(3):
         ops.ctc_loss_grad(probs, labels, ll, il, False)
 elif what == "lstm_tc":
-    B, T, H = 256, 200, 500
+    B, T, H = 256, 1000, 500
     gates = torch.randn(B * T, 8 * H, device=dev) * 0.5
     U = torch.randn(2, H, 4 * H, device=dev) / H ** 0.5
     for _ in range(2):
