@@ -38,7 +38,9 @@ struct A32Params {
   int lda, ldc, M, Nv, K, BN, nvar, ntile, rows_per_seq, row_shift, transA, aligned4;
   int kb_total, kb_per_split, stages, use_atomic, tmem_cols;
   long long* trace;     // debug (GR_A32_TRACE): clock64 stamps [cta][k-block < 64][8]
-  int splits, tiles_n, ntiles_total;   // tile t = ((m tile * tiles_n) + (variant, n tile)) * splits + k split
+  int splits, tiles_n, ntiles_total;   // tile t = ((m tile * tiles_n) + (variant group, n tile)) * splits + k split
+  int nvg;   // variants per CTA: 4 when the variant is <= 128 columns wide (one loaded A tile, four masked
+             // conversions, four 128-column accumulators), else 1 (two 256-column accumulators, double buffered)
 };
 
 #define A32_TRACE(slot, it) do { if (p.trace && (it) < 64) p.trace[((size_t)blockIdx.x * 64 + (it)) * 16 + (slot)] = clock64(); } while (0)
@@ -96,7 +98,7 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
   const int z_ = (t) % p.splits;                                              \
   const int nv_ = ((t) / p.splits) % p.tiles_n;                               \
   const int m0 = ((t) / p.splits / p.tiles_n) * 128;                          \
-  const int var = nv_ / p.ntile, n0 = (nv_ % p.ntile) * BN;                   \
+  const int var = (nv_ / p.ntile) * p.nvg, n0 = (nv_ % p.ntile) * BN;         \
   const int kb_begin = z_ * p.kb_per_split;                                   \
   const int nkb = min(kb_begin + p.kb_per_split, p.kb_total) - kb_begin;
 
@@ -124,20 +126,21 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
     for (int tile = blockIdx.x; tile < p.ntiles_total; tile += gridDim.x) {
       A32_TILE_DECODE(tile)
       (void)m0;
-      for (int i = 0; i < nkb; ++i, ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        if (lane == 0) A32_TRACE(6, it);
-        if (a32_elect_one()) {
-          uint8_t* st = smem + (size_t)s * stage_bytes + 2 * a_bytes;
-          mbar_expect_tx(&fullB[s], 2 * b_bytes);
-          const int k0 = (kb_begin + i) * kBK;
-          tma_load_2d(st, &tmBh, &fullB[s], k0, var * p.Nv + n0);
-          tma_load_2d(st + b_bytes, &tmBl, &fullB[s], k0, var * p.Nv + n0);
+      for (int i = 0; i < nkb; ++i)
+        for (int vi = 0; vi < p.nvg; ++vi, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          if (lane == 0) A32_TRACE(6, it);
+          if (a32_elect_one()) {
+            uint8_t* st = smem + (size_t)s * stage_bytes + 2 * a_bytes;
+            mbar_expect_tx(&fullB[s], 2 * b_bytes);
+            const int k0 = (kb_begin + i) * kBK;
+            tma_load_2d(st, &tmBh, &fullB[s], k0, (var + vi) * p.Nv + n0);
+            tma_load_2d(st + b_bytes, &tmBl, &fullB[s], k0, (var + vi) * p.Nv + n0);
+          }
+          __syncwarp();
         }
-        __syncwarp();
-      }
     }
   } else if (warp == 1) {
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -145,37 +148,39 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
     for (int tile = blockIdx.x; tile < p.ntiles_total; tile += gridDim.x, ++lt) {
       A32_TILE_DECODE(tile)
       (void)m0; (void)var; (void)n0;
-      const int buf = lt & 1;
-      const uint32_t acc = tmem_base + (uint32_t)(buf * 256);
-      mbar_wait(&tmem_empty[buf], (uint32_t)(((lt >> 1) & 1) ^ 1));   // epilogue drained this accumulator
+      const int nbuf = p.nvg == 1 ? 2 : 1;
+      const int buf = lt % nbuf;
+      mbar_wait(&tmem_empty[buf], (uint32_t)(((lt / nbuf) & 1) ^ 1));   // epilogue drained the accumulator(s)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int i = 0; i < nkb; ++i, ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(&fullB[s], ph);
-        if (lane == 0) A32_TRACE(3, it);
-        mbar_wait(&fullA[s], ph);
-        if (lane == 0) A32_TRACE(4, it);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint64_t dAh = make_sw128_desc(sa);
-        const uint64_t dAl = make_sw128_desc(sa + a_bytes);
-        const uint64_t dBh = make_sw128_desc(sa + 2 * a_bytes);
-        const uint64_t dBl = make_sw128_desc(sa + 2 * a_bytes + b_bytes);
-        if (a32_elect_one()) {
+      for (int i = 0; i < nkb; ++i)
+        for (int vi = 0; vi < p.nvg; ++vi, ++it) {
+          const uint32_t acc = tmem_base + (uint32_t)(p.nvg == 1 ? buf * 256 : vi * 128);
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(&fullB[s], ph);
+          if (lane == 0) A32_TRACE(3, it);
+          mbar_wait(&fullA[s], ph);
+          if (lane == 0) A32_TRACE(4, it);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint64_t dAh = make_sw128_desc(sa);
+          const uint64_t dAl = make_sw128_desc(sa + a_bytes);
+          const uint64_t dBh = make_sw128_desc(sa + 2 * a_bytes);
+          const uint64_t dBl = make_sw128_desc(sa + 2 * a_bytes + b_bytes);
+          if (a32_elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t adv = (uint64_t)(k * 2);
-            umma_bf16(acc, dAh + adv, dBh + adv, idesc, (i > 0 || k > 0) ? 1u : 0u);
-            umma_bf16(acc, dAh + adv, dBl + adv, idesc, 1u);
-            umma_bf16(acc, dAl + adv, dBh + adv, idesc, 1u);
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t adv = (uint64_t)(k * 2);
+              umma_bf16(acc, dAh + adv, dBh + adv, idesc, (i > 0 || k > 0) ? 1u : 0u);
+              umma_bf16(acc, dAh + adv, dBl + adv, idesc, 1u);
+              umma_bf16(acc, dAl + adv, dBh + adv, idesc, 1u);
+            }
+            umma_commit(&empty[s]);
+            if (i == nkb - 1 && vi == p.nvg - 1) umma_commit(&tmem_full[buf]);
           }
-          umma_commit(&empty[s]);
-          if (i == nkb - 1) umma_commit(&tmem_full[buf]);
+          __syncwarp();
+          if (lane == 0) A32_TRACE(5, it);
         }
-        __syncwarp();
-        if (lane == 0) A32_TRACE(5, it);
-      }
     }
   } else if (warp < 10) {
     // =============== A producers: 8 warps, 256 threads ===============
@@ -217,13 +222,55 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
           mB = kv ? __ldg(reinterpret_cast<const float4*>(mpB + koff)) : zero4;
         }
       };
+      if (p.nvg > 1) {
+        // ---- several variants per CTA: the fp32 tile of k-block i is loaded ONCE and converted nvg
+        //      times, each time under the dropout mask of one variant (masks prefetched one ahead)
+        auto ldmask = [&](int q, float4& mA, float4& mB) {
+          const int i = q / p.nvg, vi = q - i * p.nvg;
+          const int koff = (kb_begin + i) * kBK;
+          const bool kv = koff + kq * 4 < p.K;
+          const long long vo = (long long)vi * p.mask_var_stride;
+          mA = kv ? __ldg(reinterpret_cast<const float4*>(mpA + vo + koff)) : zero4;
+          mB = kv ? __ldg(reinterpret_cast<const float4*>(mpB + vo + koff)) : zero4;
+        };
+        auto ldx = [&](int i) {
+          const int koff = (kb_begin + i) * kBK;
+          const bool kv = koff + kq * 4 < p.K;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xa[j] = (kv && rok[j]) ? __ldg(reinterpret_cast<const float4*>(ap[j] + koff)) : zero4;
+        };
+        const int Q = nkb * p.nvg;
+        float4 mAn = one4, mBn = one4;
+        if (nkb > 0) { ldx(0); ldmask(0, mAa, mBa); }
+        int vi = 0, i = 0;
+        for (int q = 0; q < Q; ++q, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          uint8_t* Ah = smem + (size_t)s * stage_bytes + off0;
+          uint8_t* Al = Ah + a_bytes;
+          if (q + 1 < Q) ldmask(q + 1, mAn, mBn);
+          if (t == 0) A32_TRACE(0, it);
+          mbar_wait(&empty[s], ph ^ 1);
+          if (t == 0) A32_TRACE(1, it);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 x = xa[j];
+            const float4 mm = selB[j] ? mBa : mAa;
+            x.x *= mm.x; x.y *= mm.y; x.z *= mm.z; x.w *= mm.w;
+            uint32_t h01, l01, h23, l23;
+            split_pair(x.x, x.y, h01, l01);
+            split_pair(x.z, x.w, h23, l23);
+            *reinterpret_cast<uint2*>(Ah + j * 2048) = make_uint2(h01, h23);
+            *reinterpret_cast<uint2*>(Al + j * 2048) = make_uint2(l01, l23);
+          }
+          if (++vi == p.nvg) { vi = 0; ++i; if (i < nkb) ldx(i); }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
+          if (t == 0) A32_TRACE(2, it);
+          mAa = mAn; mBa = mBn;
+        }
+      } else {
       if (nkb > 0) { ld(0, 0, xa, mAa, mBa); ld(0, 4, xa, mAa, mBa); }
-      // one k-block: prefetch block i+1 into `nx`, convert block i from `cx`.  The two register
-      // buffers are selected STATICALLY (a runtime `odd ? xb : xa` select reads both operands and so
-      // waits for the prefetch it was meant to overlap).
-      // ONE register buffer: the loads of block i+1 are issued right after block i has been
-      // converted and are in flight while this thread waits for the next free stage (a second
-      // buffer does not fit 128 registers: ptxas then sinks the prefetch next to its use)
       for (int i = 0; i < nkb; ++i, ++it) {
         const int s = it % p.stages;
         const uint32_t ph = (it / p.stages) & 1;
@@ -254,6 +301,7 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
         if (t == 0) A32_TRACE(12, it);
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
         if (t == 0) A32_TRACE(2, it);
+      }
       }
     } else if constexpr (MODE == 2) {
       // ---------------- fast transposed producer ----------------
@@ -295,6 +343,58 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
         }
       };
       ma[0] = ma[1] = one4;
+      if (p.nvg > 1) {
+        // ---- several variants per CTA (see MODE 1): one load of the k-block, nvg masked conversions
+        auto ldmask = [&](int q, float4* mk) {
+          const int i = q / p.nvg, vi = q - i * p.nvg;
+          const int seq0 = ((kb_begin + i) * kBK) / T_;
+          const float* mvv = mv + (long long)vi * p.mask_var_stride;
+#pragma unroll
+          for (int sI = 0; sI < 2; ++sI)
+            mk[sI] = mok ? __ldg(reinterpret_cast<const float4*>(mvv + (size_t)min(seq0 + sI, nseq - 1) * p.M + m0 + rloc)) : zero4;
+        };
+        float4 mn[2] = {one4, one4};
+        float4 dummy[2];
+        const int Q = nkb * p.nvg;
+        if (nkb > 0) { ld(0, xa, dummy, selA_mask); ldmask(0, ma); }
+        int vi = 0, i = 0;
+        for (int q = 0; q < Q; ++q, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          uint8_t* Ah = smem + (size_t)s * stage_bytes;
+          uint8_t* Al = Ah + a_bytes;
+          if (q + 1 < Q) ldmask(q + 1, mn);
+          if (t == 0) A32_TRACE(0, it);
+          mbar_wait(&empty[s], ph ^ 1);
+          if (t == 0) A32_TRACE(1, it);
+          const float4 m_0 = ma[0], m_1 = ma[1];
+          const int sel = selA_mask;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float mg0 = g == 0 ? m_0.x : g == 1 ? m_0.y : g == 2 ? m_0.z : m_0.w;
+            const float mg1 = g == 0 ? m_1.x : g == 1 ? m_1.y : g == 2 ? m_1.z : m_1.w;
+            uint32_t hh[4], ll[4];
+#pragma unroll
+            for (int kk = 0; kk < 8; kk += 2) {
+              const float4 v0 = xa[kk], v1 = xa[kk + 1];
+              const float e0 = g == 0 ? v0.x : g == 1 ? v0.y : g == 2 ? v0.z : v0.w;
+              const float e1 = g == 0 ? v1.x : g == 1 ? v1.y : g == 2 ? v1.z : v1.w;
+              const float a0 = e0 * (((sel >> kk) & 1) ? mg1 : mg0);
+              const float a1 = e1 * (((sel >> (kk + 1)) & 1) ? mg1 : mg0);
+              split_pair(a0, a1, hh[kk >> 1], ll[kk >> 1]);
+            }
+            const uint32_t r = (uint32_t)(rloc + g);
+            const uint32_t off = r * 128u + (((uint32_t)kc ^ (r & 7u)) << 4);
+            *reinterpret_cast<uint4*>(Ah + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<uint4*>(Al + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+          }
+          if (++vi == p.nvg) { vi = 0; ++i; if (i < nkb) ld(i, xa, dummy, selA_mask); }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
+          if (t == 0) A32_TRACE(2, it);
+          ma[0] = mn[0]; ma[1] = mn[1];
+        }
+      } else {
       if (nkb > 0) ld(0, xa, ma, selA_mask);
       for (int i = 0; i < nkb; ++i, ++it) {
         const int s = it % p.stages;
@@ -329,6 +429,7 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
         if (t == 0) A32_TRACE(2, it);
+      }
       }
     } else {
     constexpr int NV = 8;            // float4 per thread per k-block (128 x 64 floats / 256 threads / 4)
@@ -441,15 +542,17 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
     for (int tile = blockIdx.x; tile < p.ntiles_total; tile += gridDim.x, ++lt) {
       A32_TILE_DECODE(tile)
       (void)nkb;
-      const int buf = lt & 1;
-      mbar_wait(&tmem_full[buf], (uint32_t)((lt >> 1) & 1));
+      const int nbuf = p.nvg == 1 ? 2 : 1;
+      const int buf = lt % nbuf;
+      mbar_wait(&tmem_full[buf], (uint32_t)((lt / nbuf) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int row = m0 + (int)r;
-      const int cbase = var * p.Nv + n0;     // first output column of this tile
       const bool add_bias = p.bias != nullptr && z_ == 0;
+      for (int vi = 0; vi < p.nvg; ++vi)
       for (int c0 = 0; c0 < BN && n0 + c0 < p.Nv; c0 += 32) {
+        const int cbase = (var + vi) * p.Nv + n0;     // first output column of this tile / variant
         uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + c0);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((p.nvg == 1 ? buf * 256 : vi * 128) + c0);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -493,7 +596,7 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           asm volatile("bar.sync 2, 128;" ::: "memory");
           if (et == 0) {
-            a32_tma_store_3d(&tmC, stg, n0 + c0, m0, var);
+            a32_tma_store_3d(&tmC, stg, n0 + c0, m0, var + vi);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           ++cc;
@@ -549,7 +652,19 @@ extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shif
   p.ntile = (Nv + p.BN - 1) / p.BN;
   p.kb_total = (K + kBK - 1) / kBK;
   const int mt = (M + 127) / 128;
-  const long long tiles = (long long)mt * p.ntile * nvar;
+  int mode = 0;
+  const char* force = getenv("GR_A32_MODE");
+  if (!transA && p.aligned4 && (!mask || rows_per_seq >= 128)) mode = 1;
+  if (transA && p.aligned4 && rows_per_seq >= 64) mode = 2;
+  if (force && force[0] == '0') mode = 0;
+  const char* nvg_env = getenv("GR_A32_NVG");
+  // measured (scripts/trace_a32.py): sharing the loaded tile pays for the transposed operand (dW: 1.57 ->
+  // 1.32 ms per 64K rows), not for the row-major one (2 086 vs 1 935 cycles per stage: its half-tile
+  // prefetch already hides the loads, and both are near the shared-memory bandwidth bound); GR_A32_NVG=4
+  // forces it there too, GR_A32_NVG=1 disables it
+  const bool nvg_ok = mode != 0 && mask && (nvar % 4) == 0 && p.ntile == 1 && p.BN <= 128;
+  p.nvg = nvg_ok && ((mode == 2 && !(nvg_env && nvg_env[0] == '1')) || (nvg_env && nvg_env[0] == '4')) ? 4 : 1;
+  const long long tiles = (long long)mt * p.ntile * (nvar / p.nvg);
   int splits = 1;
   const int sms = num_sms();
   if (tiles < sms && p.kb_total >= 8) {
@@ -569,7 +684,7 @@ extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shif
     p.trace = g_a32_trace;
   }
   p.splits = splits;
-  p.tiles_n = p.ntile * nvar;
+  p.tiles_n = p.ntile * (nvar / p.nvg);
   p.ntiles_total = (int)(tiles * splits);
   const size_t stage_bytes = 2 * ((size_t)128 * kBK * 2 + (size_t)p.BN * kBK * 2);
   int stages = (int)((227 * 1024 - 1024 - 2 * kEpiStage - 256) / stage_bytes);
@@ -593,11 +708,6 @@ extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shif
     tC = tBh;   // unused by the atomic epilogue
   }
   dim3 grid((unsigned)min((long long)sms, tiles * splits));
-  int mode = 0;
-  const char* force = getenv("GR_A32_MODE");
-  if (!transA && p.aligned4 && (!mask || rows_per_seq >= 128)) mode = 1;
-  if (transA && p.aligned4 && rows_per_seq >= 64) mode = 2;
-  if (force && force[0] == '0') mode = 0;
   if (mode == 1) {
     GR_CUDA(cudaFuncSetAttribute(gemm_a32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gemm_a32_kernel<1><<<grid, kA32Threads, smem, s>>>(tBh, tBl, tC, p);

@@ -7,8 +7,8 @@ import numpy as np, torch
 from mgr_b200 import ops, layers, _lib
 dev = torch.device("cuda:0")
 what = sys.argv[1] if len(sys.argv) > 1 else "fwd"
-if what == "fwd":
-    BT, T, F, H = 65536, 1000, 1000, 500
+if what in ("fwd", "ffwd"):
+    BT, T, F, H = (65536, 1000, 1000, 500) if what == "fwd" else (65536, 1000, 1600, 100)
     x = torch.randn(BT, F, device=dev); W = torch.randn(F, 8 * H, device=dev) * 0.05; b = torch.zeros(8 * H, device=dev)
     masks = ((torch.rand(8, BT // T + 1, F, device=dev) > 0.5).float() * 2).contiguous()
     run = lambda: layers._project(x, W, b, masks, BT // T, T, H)

@@ -131,3 +131,13 @@ def test_fused_prologue_weight_gradient(cuda, BT, T, F, H, masked):
         refU = Hp.reshape(BT, H).T @ dP.double()[:, d * 4 * H:(d + 1) * 4 * H]
         torch.cuda.synchronize()
         assert (dU.double() - refU).abs().max().item() <= 3e-5 * refU.abs().max().item()
+
+
+@pytest.mark.parametrize("nvg", ["1", "4"])
+def test_projection_variant_grouping(cuda, monkeypatch, nvg):
+    """Both tile schedules of the fused projection (one variant per CTA / four variants sharing one
+    loaded A tile, GR_A32_NVG) give the same parity, row-major and transposed."""
+    monkeypatch.setenv("GR_A32_NVG", nvg)
+    test_fused_prologue_projection(cuda, 384, 48, 1600, 100, 8)
+    test_fused_prologue_projection(cuda, 1000, 200, 1600, 100, 8)
+    test_fused_prologue_weight_gradient(cuda, 384, 96, 1600, 100, True)
