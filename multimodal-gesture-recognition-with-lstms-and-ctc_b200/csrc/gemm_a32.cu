@@ -26,7 +26,8 @@
 
 namespace gr {
 
-static constexpr int kA32Threads = 448;  // TMA warp, MMA warp, 8 A-producer warps, 4 epilogue warps
+static constexpr int kA32Threads = 480;  // TMA warp, MMA warp, 8 A-producer warps, 4 epilogue warps, tile scheduler
+static constexpr int kSchedDepth = 4;    // tile ids in flight between the scheduler and the 14 consumer warps
 static constexpr uint32_t kEpiStage = 16384;   // 128 rows x 32 fp32, SWIZZLE_128B, two buffers
 
 struct A32Params {
@@ -39,6 +40,7 @@ struct A32Params {
   int kb_total, kb_per_split, stages, use_atomic, tmem_cols;
   long long* trace;     // debug (GR_A32_TRACE): clock64 stamps [cta][k-block < 64][8]
   int splits, tiles_n, ntiles_total;   // tile t = ((m tile * tiles_n) + (variant group, n tile)) * splits + k split
+  unsigned* sched;   // dynamic tile counter (zeroed per launch): CTAs that get an SM late find less work
   int nvg;   // variants per CTA: 4 when the variant is <= 128 columns wide (one loaded A tile, four masked
              // conversions, four 128-column accumulators), else 1 (two 256-column accumulators, double buffered)
 };
@@ -90,10 +92,24 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
   uint64_t* empty = fullB + p.stages;
   uint64_t* tmem_full = empty + p.stages;    // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* sfull = tmem_empty + 2;          // [kSchedDepth] tile id published
+  uint64_t* sempty = sfull + kSchedDepth;    // [kSchedDepth] tile id read by all 14 consumer warps
+  int* tile_ring = reinterpret_cast<int*>(sempty + kSchedDepth);
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tile_ring + kSchedDepth);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // tile decode (identical in every role): t -> (m0, var, n0, k-block range)
+// every consumer warp walks the same tile sequence, published by the scheduler warp through a small ring
+#define A32_NEXT_TILE(n, tile)                                                 \
+  int tile;                                                                    \
+  {                                                                            \
+    const int sl_ = (n) % kSchedDepth;                                         \
+    mbar_wait(&sfull[sl_], (uint32_t)(((n) / kSchedDepth) & 1));              \
+    tile = tile_ring[sl_];                                                     \
+    __syncwarp();                                                              \
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sempty[sl_])) : "memory"); \
+  }                                                                            \
+  if (tile < 0) break;
 #define A32_TILE_DECODE(t)                                                    \
   const int z_ = (t) % p.splits;                                              \
   const int nv_ = ((t) / p.splits) % p.tiles_n;                               \
@@ -108,6 +124,7 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
     for (int s = 0; s < p.stages; ++s) { mbar_init(&fullA[s], 256); mbar_init(&fullB[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+    for (int b = 0; b < kSchedDepth; ++b) { mbar_init(&sfull[b], 1); mbar_init(&sempty[b], 14); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -123,7 +140,8 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
     // ---- B operand: two TMA requests (hi, lo) per k-block; the whole warp runs the loop with
     // warp-uniform operands, one elected lane issues (no R2UR waterfall around UTMALDG)
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles_total; tile += gridDim.x) {
+    for (int tn = 0;; ++tn) {
+      A32_NEXT_TILE(tn, tile)
       A32_TILE_DECODE(tile)
       (void)m0;
       for (int i = 0; i < nkb; ++i)
@@ -145,7 +163,8 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
   } else if (warp == 1) {
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     int it = 0, lt = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles_total; tile += gridDim.x, ++lt) {
+    for (;; ++lt) {
+      A32_NEXT_TILE(lt, tile)
       A32_TILE_DECODE(tile)
       (void)m0; (void)var; (void)n0;
       const int nbuf = p.nvg == 1 ? 2 : 1;
@@ -186,7 +205,8 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
     // =============== A producers: 8 warps, 256 threads ===============
     const int t = threadIdx.x - 64;  // 0..255
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles_total; tile += gridDim.x) {
+    for (int tn = 0;; ++tn) {
+    A32_NEXT_TILE(tn, tile)
     A32_TILE_DECODE(tile)
     (void)n0;
     const float* mv = p.mask ? p.mask + (long long)var * p.mask_var_stride : nullptr;
@@ -533,13 +553,14 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
     }
     }
     }  // tile loop (producers)
-  } else {
+  } else if (warp < 14) {
     // =============== epilogue: 4 warps; warp q owns TMEM lanes (= tile rows) 32q..32q+31 ===============
     const int q = warp & 3;           // warps 10..13 -> 2, 3, 0, 1: any bijection onto the lane groups works
     const int et = (int)threadIdx.x - 320;   // 0..127
     const uint32_t r = (uint32_t)(q * 32 + lane);   // row inside the tile
     int lt = 0, cc = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles_total; tile += gridDim.x, ++lt) {
+    for (;; ++lt) {
+      A32_NEXT_TILE(lt, tile)
       A32_TILE_DECODE(tile)
       (void)nkb;
       const int nbuf = p.nvg == 1 ? 2 : 1;
@@ -607,6 +628,19 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
     }
     if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else {
+    // =============== tile scheduler: first tile = blockIdx.x, then an atomic counter ===============
+    if (lane == 0) {
+      for (int n = 0;; ++n) {
+        const int sl = n % kSchedDepth;
+        mbar_wait(&sempty[sl], (uint32_t)(((n / kSchedDepth) & 1) ^ 1));
+        int tile = n == 0 ? (int)blockIdx.x : (int)(gridDim.x + atomicAdd(p.sched, 1u));
+        if (tile >= p.ntiles_total) tile = -1;
+        tile_ring[sl] = tile;
+        asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sfull[sl])) : "memory");
+        if (tile < 0) break;
+      }
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -619,6 +653,9 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
 }  // namespace gr
 
 static long long* g_a32_trace = nullptr;
+static unsigned* g_a32_sched = nullptr;     // ring of per-launch tile counters
+static unsigned g_a32_sched_next = 0;
+static constexpr unsigned kSchedSlots = 256;
 extern "C" int gr_debug_a32_trace(long long* host_out, size_t n) {
   if (!g_a32_trace) return -1;
   return cudaMemcpy(host_out, g_a32_trace, n * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
@@ -677,6 +714,9 @@ extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shif
   const bool tma_ok = (ldc % 4) == 0 && (Nv % 4) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
   p.use_atomic = (splits > 1 || accumulate || !tma_ok) ? 1 : 0;
   if (p.use_atomic && !accumulate) GR_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)nvar * Nv * 4, M, s));
+  if (!g_a32_sched) GR_CUDA(cudaMalloc(&g_a32_sched, kSchedSlots * sizeof(unsigned)));
+  p.sched = g_a32_sched + (__atomic_fetch_add(&g_a32_sched_next, 1u, __ATOMIC_RELAXED) % kSchedSlots);
+  GR_CUDA(cudaMemsetAsync(p.sched, 0, sizeof(unsigned), s));
   p.trace = nullptr;
   if (getenv("GR_A32_TRACE")) {
     if (!g_a32_trace) GR_CUDA(cudaMalloc(&g_a32_trace, (size_t)160 * 64 * 16 * 8));
@@ -687,12 +727,12 @@ extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shif
   p.tiles_n = p.ntile * (nvar / p.nvg);
   p.ntiles_total = (int)(tiles * splits);
   const size_t stage_bytes = 2 * ((size_t)128 * kBK * 2 + (size_t)p.BN * kBK * 2);
-  int stages = (int)((227 * 1024 - 1024 - 2 * kEpiStage - 256) / stage_bytes);
+  int stages = (int)((227 * 1024 - 1024 - 2 * kEpiStage - 384) / stage_bytes);
   if (stages > 4) stages = 4;
   if (stages < 2) return set_error(GR_EUNSUPPORTED, "gemm_a32: tile does not fit shared memory");
   p.stages = stages;
   p.tmem_cols = 512;   // two accumulators of <= 256 columns
-  const size_t smem = 1024 + stages * stage_bytes + 2 * kEpiStage + (3 * stages + 4) * 8 + 16;
+  const size_t smem = 1024 + stages * stage_bytes + 2 * kEpiStage + (3 * stages + 4 + 2 * kSchedDepth) * 8 + kSchedDepth * 4 + 16;
   CUtensorMap tBh, tBl, tC;
   int rc;
   if ((rc = make_map(&tBh, b_hi, (uint64_t)nvar * Nv, ldb, ldb, p.BN)) != GR_OK) return rc;
