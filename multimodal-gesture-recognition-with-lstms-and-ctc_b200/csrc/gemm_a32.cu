@@ -40,6 +40,10 @@ struct A32Params {
   int kb_total, kb_per_split, stages, use_atomic, tmem_cols;
   long long* trace;     // debug (GR_A32_TRACE): clock64 stamps [cta][k-block < 64][8]
   int splits, tiles_n, ntiles_total;   // tile t = ((m tile * tiles_n) + (variant group, n tile)) * splits + k split
+  int epi_bufs;      // epilogue staging buffers (2, 4 or 6): TMA stores in flight per CTA
+  int epi_stg;       // 1 (GR_A32_EPI=stg): the epilogue warps write the staged chunk themselves (128-byte rows,
+                     // coalesced st.global) instead of a TMA tensor store; measured slower (0.83 vs 0.73 ms on the
+                     // K = 40 store stream), kept as a cross-check of the TMA path
   unsigned* sched;   // dynamic tile counter (zeroed per launch): CTAs that get an SM late find less work
   int nvg;   // variants per CTA: 4 when the variant is <= 128 columns wide (one loaded A tile, four masked
              // conversions, four 128-column accumulators), else 1 (two 256-column accumulators, double buffered)
@@ -86,8 +90,8 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
   const uint32_t a_bytes = 128 * kBK * 2;
   const uint32_t b_bytes = (uint32_t)BN * kBK * 2;
   const uint32_t stage_bytes = 2 * (a_bytes + b_bytes);     // a multiple of 1024 (BN % 16 == 0)
-  uint8_t* epi = smem + (size_t)p.stages * stage_bytes;     // 2 x kEpiStage
-  uint64_t* fullA = reinterpret_cast<uint64_t*>(epi + 2 * kEpiStage);
+  uint8_t* epi = smem + (size_t)p.stages * stage_bytes;     // epi_bufs x kEpiStage
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(epi + (size_t)p.epi_bufs * kEpiStage);
   uint64_t* fullB = fullA + p.stages;
   uint64_t* empty = fullB + p.stages;
   uint64_t* tmem_full = empty + p.stages;    // [2]
@@ -565,7 +569,9 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
       (void)nkb;
       const int nbuf = p.nvg == 1 ? 2 : 1;
       const int buf = lt % nbuf;
+      if (et == 0) A32_TRACE(13, lt);
       mbar_wait(&tmem_full[buf], (uint32_t)((lt / nbuf) & 1));
+      if (et == 0) A32_TRACE(14, lt);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int row = m0 + (int)r;
       const bool add_bias = p.bias != nullptr && z_ == 0;
@@ -599,8 +605,12 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
         } else {
           // registers -> swizzled staging (conflict-free STS.128) -> one TMA tensor store per 32
           // columns; rows >= M and columns >= Nv are clipped by the tensor map
-          uint8_t* stg = epi + (size_t)(cc & 1) * kEpiStage;
-          if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer's previous store has read it
+          uint8_t* stg = epi + (size_t)(cc % p.epi_bufs) * kEpiStage;
+          if (et == 0 && !p.epi_stg) {   // the store that used this buffer epi_bufs chunks ago has read it
+            if (p.epi_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else if (p.epi_bufs == 4) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 5;" ::: "memory");
+          }
           asm volatile("bar.sync 2, 128;" ::: "memory");
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -614,15 +624,31 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
             }
             *reinterpret_cast<float4*>(stg + r * 128u + (((uint32_t)j ^ (r & 7u)) << 4)) = o;
           }
+          if (p.epi_stg) {
+            // 8 lanes per 128-byte row, 4 rows per store instruction; the next use of this buffer is
+            // epi_bufs chunks away and ordered by the bar.sync at the top of that chunk
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            const uint32_t ch = (uint32_t)et & 7u;                    // 16-byte chunk = columns 4 ch .. 4 ch + 3
+            const bool cok = n0 + c0 + 4 * (int)ch < p.Nv;
+            float* cdst = p.C + (size_t)cbase + c0 + 4 * ch;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t rr = (uint32_t)(et >> 3) + 16u * i;      // tile row
+              const float4 o = *reinterpret_cast<const float4*>(stg + rr * 128u + ((ch ^ (rr & 7u)) << 4));
+              if (cok && m0 + (int)rr < p.M) *reinterpret_cast<float4*>(cdst + (size_t)(m0 + rr) * p.ldc) = o;
+            }
+          } else {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           asm volatile("bar.sync 2, 128;" ::: "memory");
           if (et == 0) {
             a32_tma_store_3d(&tmC, stg, n0 + c0, m0, var + vi);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+          }
           ++cc;
         }
       }
+      if (et == 0) A32_TRACE(15, lt);
       // this accumulator may be overwritten by the MMA warp (tile lt + 2)
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
@@ -727,12 +753,24 @@ extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shif
   p.tiles_n = p.ntile * (nvar / p.nvg);
   p.ntiles_total = (int)(tiles * splits);
   const size_t stage_bytes = 2 * ((size_t)128 * kBK * 2 + (size_t)p.BN * kBK * 2);
+  // single-k-block problems (the K = 39 / 20 first-layer projections) are a pure store stream: one
+  // operand stage is enough, the rest of shared memory keeps more TMA stores in flight
+  p.epi_bufs = 2;
+  { const char* es = getenv("GR_A32_EPI"); p.epi_stg = (es && es[0] == 's') ? 1 : 0; }
   int stages = (int)((227 * 1024 - 1024 - 2 * kEpiStage - 384) / stage_bytes);
   if (stages > 4) stages = 4;
+  if (p.kb_total == 1 && !p.use_atomic) {
+    const char* eb = getenv("GR_A32_EPI_BUFS");
+    stages = 1;
+    p.epi_bufs = eb ? atoi(eb) : 2;   // measured: 2, 4, 6 buffers within noise (the HBM write stream is the limit)
+    if (p.epi_bufs != 2 && p.epi_bufs != 4 && p.epi_bufs != 6) p.epi_bufs = 2;
+    while (p.epi_bufs > 2 && 1024 + stage_bytes + (size_t)p.epi_bufs * kEpiStage + 512 > 227 * 1024) p.epi_bufs -= 2;
+    if (1024 + stage_bytes + (size_t)p.epi_bufs * kEpiStage + 512 > 227 * 1024) return set_error(GR_EUNSUPPORTED, "gemm_a32: tile does not fit shared memory");
+  } else
   if (stages < 2) return set_error(GR_EUNSUPPORTED, "gemm_a32: tile does not fit shared memory");
   p.stages = stages;
   p.tmem_cols = 512;   // two accumulators of <= 256 columns
-  const size_t smem = 1024 + stages * stage_bytes + 2 * kEpiStage + (3 * stages + 4 + 2 * kSchedDepth) * 8 + kSchedDepth * 4 + 16;
+  const size_t smem = 1024 + stages * stage_bytes + (size_t)p.epi_bufs * kEpiStage + (3 * stages + 4 + 2 * kSchedDepth) * 8 + kSchedDepth * 4 + 16;
   CUtensorMap tBh, tBl, tC;
   int rc;
   if ((rc = make_map(&tBh, b_hi, (uint64_t)nvar * Nv, ldb, ldb, p.BN)) != GR_OK) return rc;
@@ -747,7 +785,9 @@ extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shif
   } else {
     tC = tBh;   // unused by the atomic epilogue
   }
-  dim3 grid((unsigned)min((long long)sms, tiles * splits));
+  int grid_cap = sms;
+  if (const char* gc = getenv("GR_A32_GRID")) grid_cap = max(1, min(sms, atoi(gc)));   // scaling experiments
+  dim3 grid((unsigned)min((long long)grid_cap, tiles * splits));
   if (mode == 1) {
     GR_CUDA(cudaFuncSetAttribute(gemm_a32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gemm_a32_kernel<1><<<grid, kA32Threads, smem, s>>>(tBh, tBl, tC, p);

@@ -7,8 +7,8 @@ import numpy as np, torch
 from mgr_b200 import ops, layers, _lib
 dev = torch.device("cuda:0")
 what = sys.argv[1] if len(sys.argv) > 1 else "fwd"
-if what in ("fwd", "ffwd"):
-    BT, T, F, H = (65536, 1000, 1000, 500) if what == "fwd" else (65536, 1000, 1600, 100)
+if what in ("fwd", "ffwd", "l1"):
+    BT, T, F, H = (65536, 1000, 1000, 500) if what == "fwd" else ((65536, 1000, 1600, 100) if what == "ffwd" else (65536, 1000, 40, 500))
     x = torch.randn(BT, F, device=dev); W = torch.randn(F, 8 * H, device=dev) * 0.05; b = torch.zeros(8 * H, device=dev)
     masks = ((torch.rand(8, BT // T + 1, F, device=dev) > 0.5).float() * 2).contiguous()
     run = lambda: layers._project(x, W, b, masks, BT // T, T, H)
@@ -32,10 +32,11 @@ assert lib.gr_debug_a32_trace(buf, ctypes.c_size_t(n)) == 0
 tr = np.frombuffer(buf, dtype=np.int64).reshape(160, 64, 16)
 tr = tr[:148]
 names = ["prod: iteration start", "prod: stage empty", "prod: stored+arrived", "mma: fullB", "mma: fullA", "mma: issued+commit", "tmaB: stage empty(issue)", "-",
-         "prod: half0 converted", "prod: half0 next loads issued", "prod: half1 converted", "prod: half1 next loads issued", "prod: fence done"]
+         "prod: half0 converted", "prod: half0 next loads issued", "prod: half1 converted", "prod: half1 next loads issued", "prod: fence done",
+         "epi: tile begin (wait tmem_full)", "epi: tmem_full", "epi: tile done"]
 base = tr[:, 20:60, 0:1]
-rel = tr[:, 20:60, :13] - base
+rel = tr[:, 20:60, :16] - base
 for i, nme in enumerate(names):
     print("  %-26s med %7d" % (nme, np.median(rel[:, :, i])))
 per = np.median(np.diff(tr[:, 20:60, 2], axis=1))
-print("  cycles per k-block (producer arrive to arrive): %d ; mma commit to commit: %d" % (per, np.median(np.diff(tr[:, 20:60, 5], axis=1))))
+print("  cycles per k-block (producer arrive to arrive): %d ; mma commit to commit: %d ; epilogue tile to tile: %d" % (per, np.median(np.diff(tr[:, 20:60, 5], axis=1)), np.median(np.diff(tr[:, 20:60, 15], axis=1))))

@@ -141,3 +141,10 @@ def test_projection_variant_grouping(cuda, monkeypatch, nvg):
     test_fused_prologue_projection(cuda, 384, 48, 1600, 100, 8)
     test_fused_prologue_projection(cuda, 1000, 200, 1600, 100, 8)
     test_fused_prologue_weight_gradient(cuda, 384, 96, 1600, 100, True)
+
+
+def test_projection_epilogue_variants(cuda, monkeypatch):
+    """The TMA-store epilogue and the st.global cross-check epilogue (GR_A32_EPI=stg) agree with fp64."""
+    monkeypatch.setenv("GR_A32_EPI", "stg")
+    test_fused_prologue_projection(cuda, 256, 16, 1000, 500, 8)
+    test_fused_prologue_projection(cuda, 768, 128, 40, 500, 8)
