@@ -186,6 +186,9 @@ int gr_colsum_f32(const float* a, int R, int N, int lda, float* out, void* strea
 /* Elementwise helpers on the path: out = a + b (residual), concat along the last axis
  * (`Merge(mode='concat')`, multimodal.py:155-156: speech first). */
 int gr_add_f32(const float* a, const float* b, float* out, size_t n, void* stream);
+/* out[r, c] = a[r, c] + b[r, c] for c < cols, out with row stride ldo (floats): layers.add written into its
+ * column block of the Merge(concat) buffer (multimodal_fusion/multimodal.py:111,117,155-156). */
+int gr_add_into_f32(const float* a, const float* b, float* out, size_t rows, int cols, int ldo, void* stream);
 int gr_concat2_f32(const float* a, int Fa, const float* b, int Fb, float* out, size_t rows,
                    void* stream);
 

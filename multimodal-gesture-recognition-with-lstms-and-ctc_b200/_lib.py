@@ -53,6 +53,7 @@ _SIGNATURES = {
     "gr_dense_bwd_f32": ([_P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P], c_int),
     "gr_colsum_f32": ([_P, c_int, c_int, c_int, _P, _P], c_int),
     "gr_add_f32": ([_P, _P, _P, c_size_t, _P], c_int),
+    "gr_add_into_f32": ([_P, _P, _P, c_size_t, c_int, c_int, _P], c_int),
     "gr_concat2_f32": ([_P, c_int, _P, c_int, _P, c_size_t, _P], c_int),
     "gr_adam_step_f32": ([_P, _P, _P, _P, c_size_t, c_int, c_int, c_float, c_float, c_float, c_float, c_float,
                           c_float, c_float, c_int64, _P], c_int),

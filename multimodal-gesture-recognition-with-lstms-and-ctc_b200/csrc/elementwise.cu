@@ -66,6 +66,68 @@ __global__ void __launch_bounds__(256) dense_softmax_fwd_kernel(const float* __r
   }
 }
 
+// Thread-per-row variant (Fin % 4 == 0, 16-byte aligned rows): W^T in shared memory with rows padded to
+// CP floats and read with broadcast LDS.128, the row's dot products and its softmax stay in one thread
+// (no shuffles): ~5x fewer instructions per row than the warp-per-row kernel (1.14 -> see DESIGN 4.5).
+template <int CP>
+__global__ void __launch_bounds__(128) dense_softmax_fwd_row_kernel(const float* __restrict__ x, const float* __restrict__ mask,
+                                                                    const float* __restrict__ Wd, const float* __restrict__ bd,
+                                                                    int R, int Fin, int C, float* __restrict__ logits,
+                                                                    float* __restrict__ probs) {
+  extern __shared__ __align__(16) float ws[];  // Fin * CP, zero padded; then CP biases
+  for (int e = threadIdx.x; e < Fin * CP; e += blockDim.x) {
+    const int k = e / CP, c = e - k * CP;
+    ws[e] = c < C ? Wd[k * C + c] : 0.f;
+  }
+  float* bs = ws + Fin * CP;
+  for (int c = threadIdx.x; c < CP; c += blockDim.x) bs[c] = c < C ? bd[c] : 0.f;
+  __syncthreads();
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x) {
+    float acc[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) acc[c] = bs[c];
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)r * Fin);
+    const float4* mr = mask ? reinterpret_cast<const float4*>(mask + (size_t)r * Fin) : nullptr;
+    for (int k4 = 0; k4 < Fin / 4; ++k4) {
+      float4 xv = __ldg(xr + k4);
+      if (mr) { const float4 mv = __ldg(mr + k4); xv.x *= mv.x; xv.y *= mv.y; xv.z *= mv.z; xv.w *= mv.w; }
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4* w = reinterpret_cast<const float4*>(ws + (k4 * 4 + j) * CP);
+#pragma unroll
+        for (int c4 = 0; c4 < CP / 4; ++c4) {
+          const float4 wv = w[c4];
+          acc[4 * c4] = fmaf(xs[j], wv.x, acc[4 * c4]);
+          acc[4 * c4 + 1] = fmaf(xs[j], wv.y, acc[4 * c4 + 1]);
+          acc[4 * c4 + 2] = fmaf(xs[j], wv.z, acc[4 * c4 + 2]);
+          acc[4 * c4 + 3] = fmaf(xs[j], wv.w, acc[4 * c4 + 3]);
+        }
+      }
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < CP; ++c)
+      if (c < C) m = fmaxf(m, acc[c]);
+    float sum = 0.f;
+    float e_[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+      e_[c] = c < C ? expf(acc[c] - m) : 0.f;
+      sum += e_[c];
+    }
+    const float inv = 1.0f / sum;
+    float* lr = logits ? logits + (size_t)r * C : nullptr;
+    float* pr = probs ? probs + (size_t)r * C : nullptr;
+#pragma unroll
+    for (int c = 0; c < CP; ++c)
+      if (c < C) {
+        if (lr) lr[c] = acc[c];
+        if (pr) pr[c] = e_[c] * inv;
+      }
+  }
+}
+
 // ------------------------------------------------------------------ Dense backward
 // thread <-> input feature k; C accumulators (dWd[k,:]) and W[k,:] in registers; rows tiled by 32.
 template <int CR>
@@ -142,6 +204,20 @@ __global__ void add_kernel(const float4* __restrict__ a, const float4* __restric
   }
   if (blockIdx.x == 0)
     for (size_t i = tail0 + threadIdx.x; i < n; i += blockDim.x) ot[i] = at[i] + bt[i];
+}
+
+// out[r, col0 + c] = a[r, c] + b[r, c]: the residual add of a tower (layers.add, speech:79,
+// multimodal.py:111,117) written straight into its column block of the Merge(concat) buffer
+// (multimodal.py:155-156), so no separate concat pass reads and rewrites 3.3 GB
+__global__ void add_into_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float* __restrict__ o,
+                                size_t rows, int cols4, int ldo) {
+  const size_t total = rows * (size_t)cols4;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = e / cols4;
+    const int c = (int)(e - r * cols4);
+    const float4 u = a[e], v = b[e];
+    *reinterpret_cast<float4*>(o + r * ldo + 4 * c) = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+  }
 }
 
 __global__ void concat2_kernel(const float* __restrict__ a, int Fa, const float* __restrict__ b, int Fb,
@@ -242,6 +318,24 @@ extern "C" int gr_dense_softmax_fwd_f32(const float* x, const float* drop_mask, 
   const size_t smem = (size_t)Fin * (C | 1) * sizeof(float);
   if (smem > 220 * 1024) return set_error(GR_EUNSUPPORTED, "dense_fwd: Fin*C too large for shared memory");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool rowk = (Fin % 4) == 0 && C <= 48 && !getenv("GR_DENSE_WARP") &&
+                    ((reinterpret_cast<uintptr_t>(x) | (drop_mask ? reinterpret_cast<uintptr_t>(drop_mask) : 0)) & 15) == 0;
+  if (rowk) {
+    const int CP = C <= 24 ? 24 : 48;
+    const size_t sm2 = ((size_t)Fin * CP + CP) * sizeof(float);
+    if (sm2 <= 200 * 1024) {
+      const int g2 = min((R + 127) / 128, num_sms() * 8);
+      if (CP == 24) {
+        GR_CUDA(cudaFuncSetAttribute(dense_softmax_fwd_row_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        dense_softmax_fwd_row_kernel<24><<<g2, 128, sm2, s>>>(x, drop_mask, Wd, bd, R, Fin, C, logits, probs);
+      } else {
+        GR_CUDA(cudaFuncSetAttribute(dense_softmax_fwd_row_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        dense_softmax_fwd_row_kernel<48><<<g2, 128, sm2, s>>>(x, drop_mask, Wd, bd, R, Fin, C, logits, probs);
+      }
+      GR_CHECK_LAUNCH("dense_softmax_fwd_row_kernel");
+      return GR_OK;
+    }
+  }
   const int grid = min((R + 7) / 8, num_sms() * (smem > 100 * 1024 ? 1 : 2));
   if (C <= 32) {
     GR_CUDA(cudaFuncSetAttribute(dense_softmax_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -296,6 +390,17 @@ extern "C" int gr_add_f32(const float* a, const float* b, float* out, size_t n, 
       reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), reinterpret_cast<float4*>(out), n4, a, b, out,
       n4 * 4, n);
   GR_CHECK_LAUNCH("add_kernel");
+  return GR_OK;
+}
+
+extern "C" int gr_add_into_f32(const float* a, const float* b, float* out, size_t rows, int cols, int ldo, void* stream) {
+  using namespace gr;
+  if (!a || !b || !out || rows == 0 || cols <= 0 || ldo < cols) return set_error(GR_EINVAL, "add_into: bad argument");
+  if ((cols % 4) || (ldo % 4) || ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15))
+    return set_error(GR_EUNSUPPORTED, "add_into: cols, ldo and the pointers must be 16-byte aligned");
+  add_into_kernel<<<grid_for(rows * (size_t)(cols / 4)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), out, rows, cols / 4, ldo);
+  GR_CHECK_LAUNCH("add_into_kernel");
   return GR_OK;
 }
 

@@ -48,12 +48,16 @@ class UnimodalNet(nn.Module):
             reg["drop"] = ops.dropout_mask((B, T, 2 * self.units), self.pd, seed + 3, off, device)
         return reg
 
-    def tower(self, x, reg=None):
+    def tower(self, x, reg=None, merged=None, col0=0):
+        """GaussianNoise -> BLSTM -> BLSTM -> residual add.  With `merged` (a (B,T,Fo) buffer, inference
+        only) the add lands in columns [col0, col0 + 2*units) of it -- the fusion model's concat."""
         reg = reg or {}
         if reg.get("noise") is not None:
             x = ops.add(x, reg["noise"])
         y1 = self.blstm_1(x, reg.get("m1"))
         y2 = self.blstm_2(y1, reg.get("m2"))
+        if merged is not None:
+            return ops.add_into(y1, y2, merged, col0)
         return _add(y1, y2)
 
     def forward(self, x, reg=None):
@@ -126,8 +130,13 @@ class FusionNet(nn.Module):
         with torch.no_grad():
             # the two towers are independent until the concat (multimodal.py:109-118,155): run them on
             # two streams -- their recurrences (64 + 40 persistent CTAs) and GEMMs overlap on the 148 SMs
+            fa, fs = 2 * self.speech.units, 2 * self.skeletal.units
+            fused = fa % 4 == 0 and fs % 4 == 0   # 16-byte column blocks: the adds write the concat directly
+            merged = torch.empty(xa.shape[:2] + (fa + fs,), dtype=torch.float32, device=xa.device) if fused else None
             if os.environ.get("GR_TOWER_STREAMS", "1") == "0":
-                return ops.concat2(self.speech.tower(xa, reg.get("sp")), self.skeletal.tower(xs, reg.get("sk")))
+                ra = self.speech.tower(xa, reg.get("sp"), merged, 0)
+                rs = self.skeletal.tower(xs, reg.get("sk"), merged, fa)
+                return merged if fused else ops.concat2(ra, rs)
             cur = torch.cuda.current_stream()
             if self._streams is None:
                 self._streams = (torch.cuda.Stream(), torch.cuda.Stream())
@@ -135,12 +144,12 @@ class FusionNet(nn.Module):
             sa.wait_stream(cur)
             sb.wait_stream(cur)
             with torch.cuda.stream(sa):
-                ra = self.speech.tower(xa, reg.get("sp"))
+                ra = self.speech.tower(xa, reg.get("sp"), merged, 0)
             with torch.cuda.stream(sb):
-                rs = self.skeletal.tower(xs, reg.get("sk"))
+                rs = self.skeletal.tower(xs, reg.get("sk"), merged, fa)
             cur.wait_stream(sa)
             cur.wait_stream(sb)
-            return ops.concat2(ra, rs)
+            return merged if fused else ops.concat2(ra, rs)
 
     def forward(self, xa, xs, reg=None):
         reg = reg or {}

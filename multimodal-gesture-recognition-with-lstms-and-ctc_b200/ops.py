@@ -226,6 +226,20 @@ def add(a, b, out=None):
     return out
 
 
+def add_into(a, b, out, col0):
+    """out[..., col0:col0+F] = a + b with `out` a wider (.., Fo) buffer: the tower's residual add written into
+    its column block of the Merge(concat) buffer (gr_add_into_f32)."""
+    import ctypes
+    require_cuda(a, b, out)
+    a, b = _f32c(a), _f32c(b)
+    F, Fo = a.shape[-1], out.shape[-1]
+    if not out.is_contiguous():
+        raise _lib.GrError("add_into: out must be contiguous")
+    rows = a.numel() // F
+    call("gr_add_into_f32", ptr(a), ptr(b), ctypes.c_void_p(out.data_ptr() + 4 * col0), rows, F, Fo, stream_ptr())
+    return out
+
+
 def concat2(a, b):
     require_cuda(a, b)
     a, b = _f32c(a), _f32c(b)

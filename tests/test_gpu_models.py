@@ -114,3 +114,22 @@ def test_regularisers_statistics(cuda):
     assert abs(z.mean().item()) < 0.01 and abs(z.std().item() - 0.5) < 0.01
     m2 = ops.dropout_mask((8, 64, 1000), 0.4, seed=1, offset=64, device=cuda)
     assert not torch.equal(m, m2)
+
+
+@pytest.mark.parametrize("R,Fin,C,masked,warp", [(1000, 200, 22, True, False), (777, 1000, 44, False, False),
+                                                 (513, 600, 22, True, True), (300, 36, 5, False, False)])
+def test_dense_softmax_kernels(cuda, monkeypatch, R, Fin, C, masked, warp):
+    """Dense(C)+softmax (speech_lstm_ctc_words.py:86-90): thread-per-row and warp-per-row kernels vs fp64."""
+    from mgr_b200 import ops
+    if warp:
+        monkeypatch.setenv("GR_DENSE_WARP", "1")
+    g = torch.Generator().manual_seed(R + C)
+    x = torch.randn(R, Fin, generator=g).to(cuda)
+    W = (torch.randn(Fin, C, generator=g) * 0.1).to(cuda)
+    b = torch.randn(C, generator=g).to(cuda)
+    m = ((torch.rand(R, Fin, generator=g) > 0.5).float() * 2).to(cuda) if masked else None
+    logits, probs = ops.dense_softmax_fwd(x, W, b, m)
+    xd = x.double() * (m.double() if masked else 1.0)
+    ref = xd @ W.double() + b.double()
+    assert (logits.double() - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+    assert (probs.double() - torch.softmax(ref, -1)).abs().max().item() <= 1e-5
