@@ -67,22 +67,22 @@ __global__ void __launch_bounds__(4 * HP, 1) lstm_small_fwd_kernel(SmallParams p
       for (int g = 0; g < 4; ++g) nxt[g] = gn[(size_t)g * H];
     }
     if (s > 0 && n < H4) {
-      float acc[BS][2];
+      // packed fp32x2 FMAs (sm_100 FFMA2): half the FMA issue slots of the scalar loop
+      float2 acc[BS][2];
 #pragma unroll
-      for (int b = 0; b < BS; ++b) acc[b][0] = acc[b][1] = 0.f;
+      for (int b = 0; b < BS; ++b) acc[b][0] = acc[b][1] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int k = 0; k < HP; k += 4) {
+        const float2 u01 = make_float2(ureg[k], ureg[k + 1]), u23 = make_float2(ureg[k + 2], ureg[k + 3]);
 #pragma unroll
         for (int b = 0; b < BS; ++b) {
           const float4 h = *reinterpret_cast<const float4*>(hs + b * HP + k);
-          acc[b][0] = fmaf(h.x, ureg[k], acc[b][0]);
-          acc[b][1] = fmaf(h.y, ureg[k + 1], acc[b][1]);
-          acc[b][0] = fmaf(h.z, ureg[k + 2], acc[b][0]);
-          acc[b][1] = fmaf(h.w, ureg[k + 3], acc[b][1]);
+          acc[b][0] = __ffma2_rn(make_float2(h.x, h.y), u01, acc[b][0]);
+          acc[b][1] = __ffma2_rn(make_float2(h.z, h.w), u23, acc[b][1]);
         }
       }
 #pragma unroll
-      for (int b = 0; b < BS; ++b) zs[b * H4 + n] = acc[b][0] + acc[b][1];
+      for (int b = 0; b < BS; ++b) zs[b * H4 + n] = (acc[b][0].x + acc[b][0].y) + (acc[b][1].x + acc[b][1].y);
     }
     __syncthreads();
     if (eact) {
@@ -144,22 +144,21 @@ __global__ void __launch_bounds__(4 * HP, 1) lstm_small_bwd_kernel(SmallParams p
       dyv = p.dy[row * Y2 + (size_t)dir * H + ej];
     }
     if (sp > 0 && mact) {
-      float acc[BS][2];
+      float2 acc[BS][2];
 #pragma unroll
-      for (int b = 0; b < BS; ++b) acc[b][0] = acc[b][1] = 0.f;
+      for (int b = 0; b < BS; ++b) acc[b][0] = acc[b][1] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < HP; i += 4) {
+        const float2 u01 = make_float2(ureg[i], ureg[i + 1]), u23 = make_float2(ureg[i + 2], ureg[i + 3]);
 #pragma unroll
         for (int b = 0; b < BS; ++b) {
           const float4 g4 = *reinterpret_cast<const float4*>(dgs + b * QS + q * HP + i);
-          acc[b][0] = fmaf(g4.x, ureg[i], acc[b][0]);
-          acc[b][1] = fmaf(g4.y, ureg[i + 1], acc[b][1]);
-          acc[b][0] = fmaf(g4.z, ureg[i + 2], acc[b][0]);
-          acc[b][1] = fmaf(g4.w, ureg[i + 3], acc[b][1]);
+          acc[b][0] = __ffma2_rn(make_float2(g4.x, g4.y), u01, acc[b][0]);
+          acc[b][1] = __ffma2_rn(make_float2(g4.z, g4.w), u23, acc[b][1]);
         }
       }
 #pragma unroll
-      for (int b = 0; b < BS; ++b) part[(q * BS + b) * H + j] = acc[b][0] + acc[b][1];
+      for (int b = 0; b < BS; ++b) part[(q * BS + b) * H + j] = (acc[b][0].x + acc[b][0].y) + (acc[b][1].x + acc[b][1].y);
     }
     __syncthreads();
     if (eact) {
