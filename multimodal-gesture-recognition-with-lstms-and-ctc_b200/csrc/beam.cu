@@ -73,6 +73,12 @@ __global__ void __launch_bounds__(kBeamThreads) beam_search_kernel(BeamParams p)
   float* lps = reinterpret_cast<float*>(ibase); ibase += C;
   int* s_nleaf = ibase; ibase += 4;
   unsigned char* has_child = reinterpret_cast<unsigned char*>(ibase);                // W * C
+  int* hist = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(has_child + W * C) + 15) & ~uintptr_t(15));   // 256 digit counts
+  int* s_sel = hist + 256;                                                           // [0] selected count, [1] need, [2] stop
+  unsigned long long* s_thr = reinterpret_cast<unsigned long long*>(s_sel + 4);      // threshold prefix
+  unsigned long long* sel = s_thr + 1;                                               // NSEL selected keys
+  int NSEL = 32;
+  while (NSEL < W) NSEL <<= 1;
 
   const int Tn = p.seq_len ? max(0, min(p.seq_len[n], T)) : T;
   int32_t* pparent = p.pool_parent + (size_t)n * (T + 1) * W;
@@ -91,9 +97,8 @@ __global__ void __launch_bounds__(kBeamThreads) beam_search_kernel(BeamParams p)
     const float* row = p.lp + ((size_t)n * T + t) * C;
     for (int c = tid; c < C; c += kBeamThreads) lps[c] = row[c];
     for (int e = tid; e < W * C; e += kBeamThreads) has_child[e] = 0;
-    // sort only as many slots as this step can populate
-    int ns = 2;
-    while (ns < W + nleaf * NC) ns <<= 1;
+    // only as many key slots as this step can populate: W leaf slots + nleaf * (C-1) candidates
+    int ns = W + nleaf * NC;
     if (ns > NS) ns = NS;
     for (int e = tid; e < ns; e += kBeamThreads) keys[e] = 0ull;
     __syncthreads();
@@ -130,20 +135,83 @@ __global__ void __launch_bounds__(kBeamThreads) beam_search_kernel(BeamParams p)
       keys[i] = ((unsigned long long)dm_ord(tot) << 32) | (unsigned)(0xFFFFFFFFu - i);
     }
     __syncthreads();
-    // ---- bitonic sort, descending
-    for (int k = 2; k <= ns; k <<= 1) {
+    // ---- top-W selection.  Only the W largest keys matter and all keys are distinct, so the set is
+    // independent of the algorithm: an MSB-first radix select (8-bit digits, shared histogram) finds
+    // the W-th largest key, the <= W keys above it are compacted and only those are bitonic-sorted
+    // (a full sort of the 4096 candidate slots took ~380 k cycles per step).
+    if (tid == 0) { s_sel[0] = 0; s_sel[1] = W; s_sel[2] = 0; *s_thr = 0ull; }
+    __syncthreads();
+    for (int d = 7; d >= 0; --d) {
+      if (tid < 256) hist[tid] = 0;
+      __syncthreads();
+      const unsigned long long prefix = *s_thr;
+      const int sh = 8 * d;
+      for (int e = tid; e < ns; e += kBeamThreads) {
+        const unsigned long long k = keys[e];
+        if (k == 0ull) continue;
+        if (d < 7 && ((k ^ prefix) >> (sh + 8)) != 0ull) continue;   // not in the current prefix class
+        atomicAdd(&hist[(int)((k >> sh) & 255ull)], 1);
+      }
+      __syncthreads();
+      if (tid < 32) {
+        // digits 255 - 8*lane .. 248 - 8*lane belong to this lane; scan from the top
+        int c[8], tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { c[i] = hist[255 - (tid * 8 + i)]; tot += c[i]; }
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (tid >= o) incl += v;
+        }
+        const int need = s_sel[1];
+        const int above = incl - tot;                 // keys with a larger digit than this lane's
+        const int all = __shfl_sync(0xffffffffu, incl, 31);
+        if (all < need) {
+          // fewer than `need` keys left in this class (only possible at d == 7: fewer valid keys than W):
+          // everything valid is selected
+          if (tid == 0) { *s_thr = 1ull; s_sel[2] = 1; }
+        } else if (above < need && incl >= need) {
+          int run = above;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (run < need && run + c[i] >= need) {
+              const int g = 255 - (tid * 8 + i);
+              *s_thr = prefix | ((unsigned long long)g << sh);
+              s_sel[1] = need - run;
+              if (run + c[i] == need) s_sel[2] = 1;    // the whole digit class is in: lower digits are free
+            }
+            run += c[i];
+          }
+        }
+      }
+      __syncthreads();
+      if (s_sel[2]) break;
+    }
+    const unsigned long long thr = *s_thr;
+    for (int e = tid; e < NSEL; e += kBeamThreads) sel[e] = 0ull;
+    __syncthreads();
+    for (int e = tid; e < ns; e += kBeamThreads) {
+      const unsigned long long k = keys[e];
+      if (k != 0ull && k >= thr) sel[atomicAdd(&s_sel[0], 1)] = k;
+    }
+    __syncthreads();
+    // ---- bitonic sort of the selected keys, descending
+    for (int k = 2; k <= NSEL; k <<= 1) {
       for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = tid; i < ns; i += kBeamThreads) {
+        for (int i = tid; i < NSEL; i += kBeamThreads) {
           const int ixj = i ^ j;
           if (ixj > i) {
-            const unsigned long long a = keys[i], b = keys[ixj];
+            const unsigned long long a = sel[i], b = sel[ixj];
             const bool desc = (i & k) == 0;
-            if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
+            if (desc ? (a < b) : (a > b)) { sel[i] = b; sel[ixj] = a; }
           }
         }
         __syncthreads();
       }
     }
+    if (tid < W) keys[tid] = sel[tid];
+    __syncthreads();
     // ---- rebuild the leaf set
     if (tid < W) map[tid] = -1;
     __syncthreads();
@@ -208,7 +276,10 @@ static int beam_ns(int W, int C) {
   return ns;
 }
 static size_t beam_smem(int W, int C) {
-  return (size_t)beam_ns(W, C) * 8 + (size_t)W * 4 * (12 + 4) + (size_t)C * 4 + 16 + (size_t)W * C + 64;
+  int nsel = 32;
+  while (nsel < W) nsel <<= 1;
+  return (size_t)beam_ns(W, C) * 8 + (size_t)W * 4 * (12 + 4) + (size_t)C * 4 + 16 + (size_t)((W * C + 15) & ~15) + 16 + 256 * 4 + 16 + 8 +
+         (size_t)nsel * 8 + 64;
 }
 
 }  // namespace gr

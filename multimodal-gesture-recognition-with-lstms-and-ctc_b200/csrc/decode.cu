@@ -18,10 +18,10 @@ __global__ void __launch_bounds__(kDecThreads)
 bestpath_kernel(const float* __restrict__ probs, int T, int C, int drop, double threshold,
                 const int32_t* __restrict__ seq_len, float eps, int32_t* __restrict__ out_ids,
                 int32_t* __restrict__ out_len, float* __restrict__ out_score) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int n = blockIdx.x;
   const int Cp = C | 1;
-  float* tile = smem;                                              // kDecThreads * Cp
+  float* tile = smem;                                              // kDecThreads * C (Cp reserved)
   int* best = reinterpret_cast<int*>(tile + kDecThreads * Cp);     // T entries: class | low<<16
   int* cnt = best + T;                                             // C running counts
   int* nlow = cnt + C;                                             // C low-confidence counts
@@ -35,13 +35,21 @@ bestpath_kernel(const float* __restrict__ probs, int T, int C, int drop, double 
   for (int t0 = 0; t0 < Tn; t0 += kDecThreads) {
     const int rows = min(kDecThreads, Tn - t0);
     const float* src = x + (size_t)(drop + t0) * C;
-    for (int e = threadIdx.x; e < rows * C; e += kDecThreads) {
-      const int r = e / C, c = e - r * C;
-      tile[r * Cp + c] = __ldg(src + e);
+    // flat copy of rows*C floats (128-bit when the tile start is 16-byte aligned: no per-element
+    // division, 4x fewer load instructions); rows are then read at stride C
+    const int tot = rows * C;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      const int tot4 = tot >> 2;
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      float4* t4 = reinterpret_cast<float4*>(tile);
+      for (int e = threadIdx.x; e < tot4; e += kDecThreads) t4[e] = __ldg(s4 + e);
+      for (int e = (tot4 << 2) + threadIdx.x; e < tot; e += kDecThreads) tile[e] = __ldg(src + e);
+    } else {
+      for (int e = threadIdx.x; e < tot; e += kDecThreads) tile[e] = __ldg(src + e);
     }
     __syncthreads();
     if (threadIdx.x < rows) {
-      const float* row = tile + threadIdx.x * Cp;
+      const float* row = tile + threadIdx.x * C;
       float m = row[0];
       int am = 0;
       for (int c = 1; c < C; ++c) {
