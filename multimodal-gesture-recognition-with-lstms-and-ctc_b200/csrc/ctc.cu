@@ -271,8 +271,10 @@ __global__ void __launch_bounds__(64) ctc_loss_grad_kernel(CtcParams p) {
 #pragma unroll
           for (int j = 0; j < K; ++j) {
             const float prevl = (j == 0) ? upv : sl[j - 1];
-            nb[j] = lse2(sb[j], prevl) + (vb[j] ? lpb : kNeg);
-            nl[j] = lse3(sl[j], sb[j], skip[j] ? prevl : kNeg) + lpl[j];
+            // lse(sl, sb, prevl) = lse(sl, lse(sb, prevl)): the inner term is the blank update anyway
+            const float tb = lse2(sb[j], prevl);
+            nb[j] = tb + (vb[j] ? lpb : kNeg);
+            nl[j] = lse2(sl[j], skip[j] ? tb : sb[j]) + lpl[j];
           }
 #pragma unroll
           for (int j = 0; j < K; ++j) { sb[j] = nb[j]; sl[j] = nl[j]; }
