@@ -266,6 +266,17 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmUh, const __grid_consta
         pre[g][0] = a.x; pre[g][1] = a.y; pre[g][2] = a.z; pre[g][3] = a.w;
         pre[g][4] = b.x; pre[g][5] = b.y; pre[g][6] = b.z; pre[g][7] = b.w;
       }
+      {
+        // The tile may be overwritten by the TMA (h chunk, async proxy) as soon as p_consumed completes,
+        // so the eight LDS must have RETURNED before the arrive, not merely been issued: consume one
+        // word of each.  (Without this some rows read h bytes instead of P: found by the run-to-run
+        // determinism check of tests/test_gpu_lstm.py::test_full_size_recurrence_properties.)
+        float chk = 0.f;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) chk += pre[g][0] + pre[g][4];
+        asm volatile("" ::"f"(chk) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads before the async-proxy overwrite (free: 0.04 us/step)
       mbar_arrive(p_consumed);
       if (s > 0) {
         mbar_wait(tmem_full, (uint32_t)((s - 1) & 1));
@@ -329,7 +340,8 @@ lstm_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmUh, const __grid_consta
         }
         if (threadIdx.x == 64) TC_TRACE(6, s);
         // the release below is cumulative over everything ordered before it by bar.sync, so the
-        // 256 publishing threads do not each need a gpu-scope fence
+        // 256 publishing threads do not each need a gpu-scope fence (a per-thread fence.acq_rel.gpu
+        // here costs 0.75 us/step and changes nothing in 160 determinism runs)
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (threadIdx.x == 64) {

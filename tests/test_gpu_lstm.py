@@ -143,3 +143,25 @@ def test_every_recurrence_implementation(cuda, monkeypatch, impl, B, T, F, H):
     assert np.abs(Wt.grad.cpu().numpy() - rdW).max() <= tol(rdW)
     assert np.abs(Ut.grad.cpu().numpy() - rdU).max() <= tol(rdU)
     assert np.abs(bt.grad.cpu().numpy() - rdb).max() <= tol(rdb)
+
+
+def test_full_size_recurrence_properties(cuda, monkeypatch):
+    """Bench-size tcgen05 recurrence (B=256, H=500; T shortened to 160 to keep the oracle out of the loop):
+    size-independent properties -- (1) batch invariance: a sequence's output does not depend on which batch
+    tile / row it sits in or on the batch size (B=256 vs the same rows run as B=40); (2) the tensor-core
+    kernel agrees with the generic fp32 kernel on the same inputs; (3) run-to-run determinism."""
+    from mgr_b200 import ops
+    B, T, H = 256, 160, 500
+    g = torch.Generator().manual_seed(11)
+    gates = (torch.randn(B * T, 8 * H, generator=g) * 0.7).to(cuda)
+    U = (torch.randn(2, H, 4 * H, generator=g) / H ** 0.5).to(cuda)
+    y_full, _ = ops.lstm_recurrence_fwd(gates.clone(), U, B, T, H, keep_cell=False)
+    y_again, _ = ops.lstm_recurrence_fwd(gates.clone(), U, B, T, H, keep_cell=False)
+    assert torch.equal(y_full, y_again)
+    rows = torch.arange(100, 140, device=cuda)                      # straddles the two 128-row batch tiles
+    sub = gates.reshape(B, T, 8 * H)[rows].reshape(-1, 8 * H).contiguous()
+    y_sub, _ = ops.lstm_recurrence_fwd(sub, U, rows.numel(), T, H, keep_cell=False)
+    assert (y_full[rows] - y_sub).abs().max().item() <= 1e-6        # only the MMA row position differs
+    monkeypatch.setenv("GR_LSTM_IMPL", "generic")
+    y_gen, _ = ops.lstm_recurrence_fwd(sub.clone(), U, rows.numel(), T, H, keep_cell=False)
+    assert (y_sub - y_gen).abs().max().item() <= 2e-4
