@@ -59,6 +59,37 @@ def test_fused_logit_mode(cuda, B, T, C, Lmax):
     assert np.abs(grad - ref_g).max() <= GRAD_TOL * np.abs(ref_g).max()
 
 
+@pytest.mark.parametrize("impl", ["v4", "v2"])
+@pytest.mark.parametrize("Tn", [1, 2, 3, 7, 31, 32, 33, 63, 64, 65, 66, 97, 128, 129])
+def test_chunk_boundaries_and_both_kernels(cuda, monkeypatch, impl, Tn):
+    """Sequence lengths around the 32-frame chunk, the meeting row t* = Tn/2 and the 4-row lattice prefetch
+    window; the previous kernel (GR_CTC_IMPL=v2) stays as a cross-check."""
+    import mgr_b200 as mgr
+    from oracle import ctc_ref
+    monkeypatch.setenv("GR_CTC_IMPL", impl)
+    B, C, Lmax, T = 3, 22, 12, 140
+    rng = np.random.default_rng(100 + Tn)
+    p, a = random_probs(rng, B, T, C)
+    il = np.full((B, 1), Tn)
+    il[1, 0] = max(1, Tn - 1)
+    labels, ll = random_labels(rng, B, Lmax, C, T_avail=np.maximum(il[:, 0], 2))
+    ll = np.minimum(ll, il)
+    labels[0, 1:] = -1
+    ll[0, 0] = 1
+    loss, grad = _run(mgr, cuda, p, labels, il, ll)
+    ref_loss, ref_g = ctc_ref.ctc_lambda_func((p, labels, il, ll), want_grad=True)
+    fin = np.isfinite(ref_loss)
+    assert np.array_equal(np.isfinite(loss), fin)
+    assert np.abs(loss[fin] - ref_loss[fin]).max() <= LOSS_RTOL * np.abs(ref_loss[fin]).max()
+    ref_g = ref_g / B
+    scale = np.abs(ref_g).max(axis=2, keepdims=True) + 1e-12
+    assert (np.abs(grad - ref_g) / scale).max() <= GRAD_TOL
+    loss2, grad2 = _run(mgr, cuda, None, labels, il, ll, logits=a)
+    ref_loss2, ref_g2 = ctc_ref.softmax_ctc_grad_logits(a, labels, il, ll)
+    assert np.abs(loss2[fin] - ref_loss2[fin]).max() <= LOSS_RTOL * np.abs(ref_loss2[fin]).max()
+    assert np.abs(grad2 - ref_g2).max() <= GRAD_TOL * np.abs(ref_g2).max()
+
+
 def test_edge_cases(cuda):
     import mgr_b200 as mgr
     from oracle import ctc_ref
