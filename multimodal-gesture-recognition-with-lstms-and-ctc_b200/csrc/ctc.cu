@@ -20,8 +20,9 @@ namespace gr {
 static constexpr float kNeg = -1.0e30f;  // "log zero": finite so that no inf-inf NaN can arise
 
 __device__ __forceinline__ float lse2(float a, float b) {
-  float hi = fmaxf(a, b), lo = fminf(a, b);
-  return hi + lg2_approx(1.0f + ex2_approx(lo - hi));
+  // lo - hi == -|a - b| exactly, so the max and the difference do not depend on each other (one
+  // instruction and one dependent latency less per call; the |.| and the sign fold into the MUFU operand)
+  return fmaxf(a, b) + lg2_approx(1.0f + ex2_approx(-fabsf(a - b)));
 }
 __device__ __forceinline__ float lse3(float a, float b, float c) {
   float hi = fmaxf(a, b), lo = fminf(a, b);
@@ -68,7 +69,6 @@ struct CtcParams {
   float* ws;
   size_t ws_seq_floats;
   int RS;  // lattice row stride (floats)
-  int post_rows;  // v4 post-pass: 1 = lane per row (index-list walk), 0 = lane per class
 };
 
 __host__ __device__ inline int ctc_cp(int C) { return C | 1; }
@@ -558,22 +558,6 @@ __global__ void __launch_bounds__(64) ctc_loss_grad_kernel(CtcParams p) {
   const float eps = p.eps;
   const bool vec2 = ((C & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 7) == 0);
   const bool gvec2 = ((C & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.grad) & 7) == 0);
-  // post-pass table (C <= 32): lane c holds the lattice-row byte offsets of the label states of class c
-  constexpr int kPMax = 6;
-  uint32_t cpos[kPMax];
-  int ccnt = 0, cfirst = 0, cmax = 0;
-#pragma unroll
-  for (int m = 0; m < kPMax; ++m) cpos[m] = 0;
-  if (gb && C <= 32 && !p.post_rows) {
-    if (lane < blank) {
-      cfirst = cstart[lane];
-      ccnt = cstart[lane + 1] - cfirst;
-#pragma unroll
-      for (int m = 0; m < kPMax; ++m)
-        if (m < ccnt) cpos[m] = 4u * (uint32_t)(Lmax + 1 + clist[cfirst + m]);
-    }
-    cmax = __reduce_max_sync(0xffffffffu, ccnt);
-  }
 
   double off = 0.0;       // states are kept relative to this running offset, re-centred once per chunk
   double logp2 = 0.0;
@@ -856,52 +840,9 @@ __global__ void __launch_bounds__(64) ctc_loss_grad_kernel(CtcParams p) {
         emit();
       }
       __syncwarp();
-      // ---- post-pass: occupancies -> gradient, in place over X.
-      if (C <= 32 && !p.post_rows) {
-        // (a) lane = row: blank occupancy of the row; (b) rows one after the other with lane = class: the
-        // positions of the lane's class sit in registers (labels are fixed per sequence), so the class sums
-        // are a handful of conflict-free loads per row instead of a walk over index lists per lane
-        float occb = 0.f;
-        if (lane < n) {
-          int sidx = slot0 + (dir == 0 ? lane : n - 1 - lane);
-          if (sidx >= EM) sidx -= EM;
-          const float* er = Es + sidx * RS;
-          for (int k = 0; k <= L; ++k) occb += er[k];
-        }
-        int sidx0 = slot0 + (dir == 0 ? 0 : n - 1);
-        if (sidx0 >= EM) sidx0 -= EM;
-        uint32_t er = e_base + (uint32_t)sidx0 * e_pitch;
-        uint32_t xa = (uint32_t)__cvta_generic_to_shared(Xs) + 4u * (uint32_t)lane;
-        const bool cact = lane < C;
-        for (int r = 0; r < n; ++r) {
-          float o = 0.f;
-#pragma unroll
-          for (int m = 0; m < kPMax; ++m)
-            if (m < cmax) { const float v = lds_f32(er + cpos[m]); o += m < ccnt ? v : 0.f; }
-          if (cmax > kPMax)
-            for (int m = kPMax; m < ccnt; ++m) o += lds_f32(er + 4u * (uint32_t)(Lmax + 1 + clist[cfirst + m]));
-          const float ob = __shfl_sync(0xffffffffu, occb, r);
-          const float Z = __shfl_sync(0xffffffffu, Zrow, r);
-          if (lane == blank) o = ob;
-          float q = 0.f, g = 0.f;
-          if (cact) q = ex2_approx(lds_f32(xa));
-          if (p.is_logits) {
-            const float gz = up_scale * (q - o);
-            const float pe = q * Z;                  // p + eps
-            const float pr = fmaxf(pe - eps, 0.f);   // p
-            const float wgz = cact ? (pr / pe) * gz : 0.f;
-            const float dot = warp_sum(wgz);
-            g = wgz - pr * dot;
-          } else {
-            g = up_scale * __fdividef(q - o, q * Z);
-          }
-          if (cact) sts_f32(xa, g);
-          xa += 4u * (uint32_t)C;
-          if (dir == 0) { er += e_pitch; if (er == e_base + e_bytes) er = e_base; }
-          else { if (er == e_base) er = e_base + e_bytes; er -= e_pitch; }
-        }
-      } else if (lane < n) {
-        // C > 32: lane = row of the chunk (natural time order), classes walked through the class-sorted index list
+      // ---- per-row post-pass: occupancies -> gradient, in place over X
+      if (lane < n) {
+        // lane = row of the chunk (natural time order), classes walked through the class-sorted index list
         float* xrow = Xs + lane * C;
         int sidx = slot0 + (dir == 0 ? lane : n - 1 - lane);
         if (sidx >= EM) sidx -= EM;
@@ -1016,7 +957,6 @@ extern "C" int gr_ctc_loss_grad_f32(const float* x, int input_is_logits, int B, 
   p.upstream = upstream; p.loss = loss; p.grad = grad_out; p.status = status;
   p.ws = static_cast<float*>(workspace);
   p.RS = ctc_row_stride(Lmax);
-  { const char* pm = getenv("GR_CTC_POST"); p.post_rows = (pm && pm[0] == 'r') ? 1 : 0; }
   p.ws_seq_floats = (size_t)(T + 2) * p.RS;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int K = (Lmax + 1 + 31) / 32;
