@@ -216,7 +216,7 @@ def ctc_microbench(dev, peak_gbs):
     return {"workload": "ctc loss+grad B=1024 T=1000 L=40 C=22 (config 4)", "ms": ms,
             "frames_per_s": frames / (ms * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                         "frac": achieved / peak_gbs, "traffic": None,
+                         "frac": achieved / peak_gbs, "traffic": read_traffic("gr_ctc_loss_grad_f32"),
                          "algorithmic_bytes_per_frame": bytes_per_frame}}
 
 

@@ -54,6 +54,10 @@ __device__ __forceinline__ void sts_f32(uint32_t a, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
 }
 
+__device__ __forceinline__ void sts_f32_if(uint32_t a, float v, bool pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.f32 [%0], %1;\n\t}" ::"r"(a), "f"(v), "r"((uint32_t)pred) : "memory");
+}
+
 struct CtcParams {
   const float* x;
   int is_logits, B, T, C, drop;
@@ -816,8 +820,8 @@ __global__ void __launch_bounds__(64) ctc_loss_grad_kernel(CtcParams p) {
         const float cb = cst - lpb;
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-          sts_f32(erow + eoffb[j], ex2_approx((sb[j] + ev_b[j]) + cb));
-          sts_f32(erow + eoffl[j], ex2_approx((sl[j] + ev_l[j]) + (cst - lpl[j])));
+          sts_f32_if(erow + eoffb[j], ex2_approx((sb[j] + ev_b[j]) + cb), vb[j]);      // (predicated, not routed to the
+          sts_f32_if(erow + eoffl[j], ex2_approx((sl[j] + ev_l[j]) + (cst - lpl[j])), vl[j]);  //  pad word: no smem race)
         }
         xrow += rstep;
         erow += e_pitch;
