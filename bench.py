@@ -288,16 +288,17 @@ def run_gpu(args):
     xa_d, xs_d = xa_h.to(dev), xs_h.to(dev)
     h2d_bytes = sum(t.numel() * t.element_size() for t in (xa_h, xs_h, lab_h, il_h, ll_h))
 
-    step_no = [0]
-
-    def train_step(xa, xs, lab, il, ll):
-        reg = model.sample_regularisers(B, T, seed=1234 + rank, step=step_no[0], device=dev)
-        loss, grads = model.loss_and_grads(xa, xs, lab, il, ll, reg, global_batch=GLOBAL_BATCH)
+    def reduce_grads(grads):
         bucket.pack(grads)
-        views = bucket.all_reduce()
-        opt.step(views)
-        step_no[0] += 1
-        return loss
+        return bucket.all_reduce()
+
+    # FusionTrainer = the reference's training step (forward, CTC objective, all-reduce, Adam/clip/maxnorm) with the
+    # frozen towers of the NEXT batch enqueued beside the fusion layer of this one (GR_PIPELINE=0: strictly serial)
+    trainer = mgr.FusionTrainer(model, opt, seed=1234 + rank, global_batch=GLOBAL_BATCH, grad_hook=reduce_grads)
+    pipeline = os.environ.get("GR_PIPELINE", "1") == "1"
+
+    def train_step(xa, xs, lab, il, ll, nxt=None, nxt_ready=None):
+        return trainer.step((xa, xs, lab, il, ll), next_inputs=nxt if pipeline else None, next_ready=nxt_ready)
 
     lab_d, il_d, ll_d = lab_h.to(dev), il_h.to(dev), ll_h.to(dev)
 
@@ -325,12 +326,13 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
     for _ in range(max(args.warmup, args.min_warmup)):
-        train_step(xa_d, xs_d, lab_d, il_d, ll_d)
+        train_step(xa_d, xs_d, lab_d, il_d, ll_d, (xa_d, xs_d))
     launches0 = _lib.launch_count
     _lib.kernel_timing_begin(["gr_lstm_recurrence_fwd_f32", "gr_lstm_recurrence_bwd_f32", "gr_gemm_bf16x3_f32",
                               "gr_ctc_loss_grad_f32", "gr_split_bf16_f32", "gr_gemm_a32_f32"])
     sampler.mark("begin")
-    total_ms = timed(lambda: train_step(xa_d, xs_d, lab_d, il_d, ll_d), args.steps)
+    # every timed step trains one batch and enqueues the towers of the next one (K tower passes + K fusion passes)
+    total_ms = timed(lambda: train_step(xa_d, xs_d, lab_d, il_d, ll_d, (xa_d, xs_d)), args.steps)
     sampler.mark("end")
     ktimes = _lib.kernel_timing_end()
     launches = _lib.launch_count - launches0
@@ -340,11 +342,28 @@ def run_gpu(args):
     # ---- end-to-end arm: pinned host inputs -> H2D every step, loss read back every step
     losses = []
 
+    copy_stream = torch.cuda.Stream()
+
+    def h2d():
+        with torch.cuda.stream(copy_stream):
+            ts = tuple(t.to(dev, non_blocking=True) for t in (xa_h, xs_h, lab_h, il_h, ll_h))
+            ev = copy_stream.record_event()
+        return ts, ev
+
+    staged = [h2d()]
+
     def e2e_step():
-        xa = xa_h.to(dev, non_blocking=True)
-        xs = xs_h.to(dev, non_blocking=True)
-        lab, il, ll = lab_h.to(dev, non_blocking=True), il_h.to(dev, non_blocking=True), ll_h.to(dev, non_blocking=True)
-        loss = train_step(xa, xs, lab, il, ll)
+        # one H2D copy of a full batch from pinned memory (on a copy stream) and one D2H read of the loss per step;
+        # with the pipeline the copy made in step n is the batch of step n+1, whose towers start as soon as it lands
+        (cur, ev) = staged[0]
+        torch.cuda.current_stream().wait_event(ev)
+        for t in cur:
+            t.record_stream(torch.cuda.current_stream())
+        staged[0] = h2d() if pipeline else (cur, ev)
+        nxt, nev = staged[0]
+        loss = train_step(*cur, nxt=(nxt[0], nxt[1]), nxt_ready=nev)
+        if not pipeline:
+            staged[0] = h2d()
         losses.append(loss.cpu())
 
     if args.skip_e2e:
@@ -403,6 +422,9 @@ def run_gpu(args):
                                    "regularisers on (Philox)", "global_batch": GLOBAL_BATCH, "per_gpu_batch": B,
                        "seq_len": T, "classes": NB_CLASSES, "parallelism": "dp%d" % world,
                        "projection_arithmetic": "bf16x3 split on tcgen05 (fp32-faithful)",
+                       "schedule": ("frozen towers of batch n+1 run beside the fusion layer of batch n "
+                                    "(FusionTrainer; every timed step = one tower pass + one fusion pass + optimiser)"
+                                    if pipeline else "serial (GR_PIPELINE=0)"),
                        "l2": "per-step activation working set (>10 GB) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "seq/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": B * 4},

@@ -8,7 +8,8 @@ from . import _lib, ops  # noqa: F401
 from ._lib import GrError, InvalidArgumentError  # noqa: F401
 from .losses import ctc_lambda_func, ctc_batch_cost, softmax_ctc  # noqa: F401
 from .layers import BidirectionalLSTM, DenseSoftmax, blstm  # noqa: F401
-from .models import SpeechNet, SkeletalNet, FusionNet, UnimodalNet, KerasAdam, fusion_optimizer  # noqa: F401
+from .models import (SpeechNet, SkeletalNet, FusionNet, UnimodalNet, KerasAdam, fusion_optimizer,  # noqa: F401
+                     FusionTrainer)
 from .sequence_decoding import decode_batch, decode_batch_speech, decode_ids, ctc_decode  # noqa: F401
 
 __version__ = "0.1.0"

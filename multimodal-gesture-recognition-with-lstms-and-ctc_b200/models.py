@@ -89,6 +89,9 @@ def SkeletalNet(numfeats=20, nb_classes=22, units=300, seed=53):
     return UnimodalNet(numfeats, units, nb_classes, noise_std=0.5, dropouts=(0.6, 0.6, 0.6), seed=seed)
 
 
+SPLIT_MIN_HALF = 64   # a half-batch speech tower still fills its 128-row MMA tile at least half
+
+
 class FusionNet(nn.Module):
     def __init__(self, speech=None, skeletal=None, nb_classes=22, units=100, seed=61):
         super().__init__()
@@ -125,31 +128,66 @@ class FusionNet(nn.Module):
         reg["drop"] = ops.dropout_mask((B, T, 2 * self.units), 0.5, seed + 31, off, device)
         return reg
 
-    def merged(self, xa, xs, reg=None):
+    def launch_towers(self, xa, xs, reg=None, ready=None):
+        """Enqueue the two frozen towers (multimodal.py:109-118) and the Merge(concat) (`:155`) WITHOUT joining
+        the calling stream: returns a handle for `join_towers`.  The towers are independent until the concat, so
+        they run on side streams; because they are frozen (`:135-148`) their output for batch n+1 does not depend
+        on the weight update of step n either, which is what `FusionTrainer` uses to run them one batch ahead.
+        `ready`: CUDA event after which xa/xs are valid (inputs copied on another stream)."""
         reg = reg or {}
         with torch.no_grad():
-            # the two towers are independent until the concat (multimodal.py:109-118,155): run them on
-            # two streams -- their recurrences (64 + 40 persistent CTAs) and GEMMs overlap on the 148 SMs
             fa, fs = 2 * self.speech.units, 2 * self.skeletal.units
             fused = fa % 4 == 0 and fs % 4 == 0   # 16-byte column blocks: the adds write the concat directly
-            merged = torch.empty(xa.shape[:2] + (fa + fs,), dtype=torch.float32, device=xa.device) if fused else None
-            if os.environ.get("GR_TOWER_STREAMS", "1") == "0":
+            if not fused or os.environ.get("GR_TOWER_STREAMS", "1") == "0":
+                if ready is not None:
+                    torch.cuda.current_stream().wait_event(ready)
+                merged = torch.empty(xa.shape[:2] + (fa + fs,), dtype=torch.float32, device=xa.device) if fused else None
                 ra = self.speech.tower(xa, reg.get("sp"), merged, 0)
                 rs = self.skeletal.tower(xs, reg.get("sk"), merged, fa)
-                return merged if fused else ops.concat2(ra, rs)
+                return {"merged": merged if fused else ops.concat2(ra, rs), "events": []}
+            merged = torch.empty(xa.shape[:2] + (fa + fs,), dtype=torch.float32, device=xa.device)
             cur = torch.cuda.current_stream()
             if self._streams is None:
-                self._streams = (torch.cuda.Stream(), torch.cuda.Stream())
-            sa, sb = self._streams
-            sa.wait_stream(cur)
-            sb.wait_stream(cur)
-            with torch.cuda.stream(sa):
-                ra = self.speech.tower(xa, reg.get("sp"), merged, 0)
-            with torch.cuda.stream(sb):
-                rs = self.skeletal.tower(xs, reg.get("sk"), merged, fa)
-            cur.wait_stream(sa)
-            cur.wait_stream(sb)
-            return merged if fused else ops.concat2(ra, rs)
+                self._streams = (torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream())
+            sa, sb, sc = self._streams
+            B = xa.shape[0]
+            work = []
+            if B >= 2 * SPLIT_MIN_HALF and os.environ.get("GR_TOWER_SPLIT", "1") == "1":
+                # The speech recurrence of a 256-sequence batch holds 128 SMs (2 directions x 2 batch tiles x 32
+                # unit slices, one CTA per SM), so the skeletal recurrence (76 CTAs) cannot run beside it.  Two
+                # half-batch speech towers (64 CTAs each) can each share the GPU with it: 55.0 -> 52.8 ms/step.
+                h = B // 2
+                sp = reg.get("sp") or {}
+
+                def half(lo, hi):
+                    return {k: (v[lo:hi] if k == "noise" else v[:, lo:hi].contiguous()) for k, v in sp.items()}
+                work = [(sa, lambda: self.speech.tower(xa[:h], half(0, h), merged[:h], 0)),
+                        (sb, lambda: self.skeletal.tower(xs, reg.get("sk"), merged, fa)),
+                        (sc, lambda: self.speech.tower(xa[h:], half(h, B), merged[h:], 0))]
+            else:
+                work = [(sa, lambda: self.speech.tower(xa, reg.get("sp"), merged, 0)),
+                        (sb, lambda: self.skeletal.tower(xs, reg.get("sk"), merged, fa))]
+            events = []
+            for s_, fn in work:
+                s_.wait_stream(cur)
+                if ready is not None:
+                    s_.wait_event(ready)
+                    xa.record_stream(s_)
+                    xs.record_stream(s_)
+                with torch.cuda.stream(s_):
+                    fn()
+                    events.append(s_.record_event())
+            return {"merged": merged, "events": events, "inputs": (xa, xs)}
+
+    @staticmethod
+    def join_towers(handle):
+        cur = torch.cuda.current_stream()
+        for ev in handle["events"]:
+            cur.wait_event(ev)
+        return handle["merged"]
+
+    def merged(self, xa, xs, reg=None):
+        return self.join_towers(self.launch_towers(xa, xs, reg))
 
     def forward(self, xa, xs, reg=None):
         reg = reg or {}
@@ -159,15 +197,16 @@ class FusionNet(nn.Module):
 
     # ------------------------------------------------------------------ explicit training step
     def loss_and_grads(self, xa, xs, labels, input_length, label_length, reg=None, global_batch=None,
-                       check=False, eps=KERAS_CTC_EPS):
+                       check=False, eps=KERAS_CTC_EPS, towers=None):
         """One forward+backward of the Keras objective mean_b ctc_loss_b (dummy loss, speech:131).
         Returns (loss (B,), [grads in trainable_parameters() order]).  `global_batch` = divisor of
-        the mean (the data-parallel global batch; default = local B)."""
+        the mean (the data-parallel global batch; default = local B).  `towers`: a `launch_towers` handle for
+        these inputs (the frozen towers already enqueued, e.g. one batch ahead)."""
         reg = reg or {}
         B, T = xa.shape[0], xa.shape[1]
         gb = float(global_batch or B)
         lab_i, il, ll = _prep_lengths(labels, input_length, label_length, xa.device)
-        m = self.merged(xa, xs, reg)
+        m = self.join_towers(towers) if towers is not None else self.merged(xa, xs, reg)
         l3 = self.blstm_3
         y3 = l3(m, reg.get("m3"))                      # autograd node (kernel-backed)
         H2 = 2 * self.units
@@ -207,6 +246,48 @@ class KerasAdam:
             ops.adam_step(p.data, g, m, v, self.iterations, self.lr, self.beta1, self.beta2, self.eps, self.decay,
                           self.clipvalue, mn)
         self.iterations += 1
+
+
+class FusionTrainer:
+    """Training loop body of multimodal.py (`fit_generator` step: forward, CTC objective, Adam/clip/maxnorm) with
+    the frozen towers pipelined ONE BATCH AHEAD: while the fusion BLSTM of batch n trains on the calling stream,
+    the towers of batch n+1 (whose weights never change, multimodal.py:135-148) already run on the side streams.
+    Regularisers are sampled per step index exactly as without the pipeline, so losses and updates are identical.
+
+        trainer = FusionTrainer(model, opt, seed=..., global_batch=...)
+        loss = trainer.step(batch_n, next_inputs=(xa_next, xs_next))     # batch = (xa, xs, labels, il, ll)
+    """
+
+    def __init__(self, model, opt, seed=0, global_batch=None, grad_hook=None):
+        self.model, self.opt, self.seed, self.global_batch = model, opt, seed, global_batch
+        self.grad_hook = grad_hook        # e.g. pack + all-reduce of the flat gradient bucket (data parallel)
+        self.step_no = 0                  # next step to be trained
+        self._pending = None              # (step index, reg, towers handle)
+
+    def _launch(self, xa, xs, step, ready=None):
+        B, T = xa.shape[0], xa.shape[1]
+        reg = self.model.sample_regularisers(B, T, seed=self.seed, step=step, device=xa.device)
+        return step, reg, self.model.launch_towers(xa, xs, reg, ready)
+
+    def step(self, batch, next_inputs=None, next_ready=None):
+        """Train on `batch`; `next_inputs` = (xa, xs) of the following batch (its towers are enqueued now),
+        `next_ready` = CUDA event after which those tensors are valid (e.g. recorded on a copy stream)."""
+        xa, xs, labels, il, ll = batch
+        pend = self._pending
+        self._pending = None
+        if pend is None or pend[0] != self.step_no or pend[2].get("inputs", (None, None))[0] is not xa \
+                or pend[2]["inputs"][1] is not xs:
+            pend = self._launch(xa, xs, self.step_no)          # cold start, or the prefetch was for other tensors
+        _, reg, towers = pend
+        if next_inputs is not None:
+            self._pending = self._launch(next_inputs[0], next_inputs[1], self.step_no + 1, next_ready)
+        loss, grads = self.model.loss_and_grads(xa, xs, labels, il, ll, reg, global_batch=self.global_batch,
+                                                towers=towers)
+        if self.grad_hook is not None:
+            grads = self.grad_hook(grads)
+        self.opt.step(grads)
+        self.step_no += 1
+        return loss
 
 
 def fusion_optimizer(model):

@@ -83,6 +83,53 @@ def test_fusion_training_step_matches_oracle(cuda):
     assert sp.blstm_1.kernel.grad is None  # frozen towers
 
 
+def test_half_batch_speech_towers_match_whole_batch(cuda, monkeypatch):
+    """GR_TOWER_SPLIT=1 runs the speech tower as two half-batch towers on two streams beside the skeletal one
+    (so the recurrences fit on the GPU together); the merged features must not depend on that (sequences are
+    independent; only the MMA row a sequence sits in changes)."""
+    import mgr_b200 as mgr
+    B, T = 128, 24
+    sp, sk, fu = _small_nets(mgr, cuda, Ha=64, Hs=48)
+    g = torch.Generator().manual_seed(5)
+    xa = torch.randn(B, T, 39, generator=g).to(cuda)
+    xs = torch.randn(B, T, 20, generator=g).to(cuda)
+    reg = fu.sample_regularisers(B, T, seed=7, step=0, device=cuda)
+    monkeypatch.setenv("GR_TOWER_SPLIT", "0")
+    whole = fu.merged(xa, xs, reg).clone()
+    monkeypatch.setenv("GR_TOWER_SPLIT", "1")
+    split = fu.merged(xa, xs, reg).clone()
+    torch.cuda.synchronize()
+    assert (whole - split).abs().max().item() <= 1e-5
+    assert whole.abs().max().item() > 1e-3
+
+
+def test_pipelined_trainer_equals_serial_steps(cuda):
+    """FusionTrainer with the towers one batch ahead must give the same losses and the same weights as the
+    plain step-by-step loop (same per-step regulariser streams; the towers are frozen)."""
+    import copy
+    import mgr_b200 as mgr
+    rng = np.random.default_rng(77)
+    B, T, C = 4, 30, 22
+    _, _, fu1 = _small_nets(mgr, cuda)
+    fu2 = copy.deepcopy(fu1)
+    batches = []
+    for _ in range(4):
+        xa = torch.tensor(rng.standard_normal((B, T, 39)).astype(np.float32), device=cuda)
+        xs = torch.tensor(rng.standard_normal((B, T, 20)).astype(np.float32), device=cuda)
+        labels, ll = random_labels(rng, B, 6, C)
+        batches.append((xa, xs, torch.tensor(labels), torch.tensor(np.full((B, 1), T - 2)), torch.tensor(ll)))
+    t1 = mgr.FusionTrainer(fu1, mgr.fusion_optimizer(fu1), seed=9, global_batch=B)
+    t2 = mgr.FusionTrainer(fu2, mgr.fusion_optimizer(fu2), seed=9, global_batch=B)
+    for n, b in enumerate(batches):
+        l1 = t1.step(b)                                                        # serial
+        nxt = batches[n + 1][:2] if n + 1 < len(batches) else None
+        l2 = t2.step(b, next_inputs=nxt)                                       # towers of batch n+1 in flight
+        assert torch.allclose(l1, l2, rtol=1e-6, atol=0)
+    # (not bit-equal: the weight-gradient GEMMs accumulate split-K tiles with fp32 atomics)
+    for p1, p2 in zip(fu1.trainable_parameters(), fu2.trainable_parameters()):
+        assert torch.allclose(p1, p2, rtol=0, atol=1e-6)
+
+
 def test_adam_clip_maxnorm_matches_keras_formula(cuda):
     import mgr_b200 as mgr
     rng = np.random.default_rng(5)
