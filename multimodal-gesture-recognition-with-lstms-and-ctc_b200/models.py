@@ -89,7 +89,7 @@ def SkeletalNet(numfeats=20, nb_classes=22, units=300, seed=53):
     return UnimodalNet(numfeats, units, nb_classes, noise_std=0.5, dropouts=(0.6, 0.6, 0.6), seed=seed)
 
 
-SPLIT_MIN_HALF = 64   # a half-batch speech tower still fills its 128-row MMA tile at least half
+SPLIT_MIN_HALF = 128   # split only batches of more than one 128-row MMA tile: each half still fills its tile
 
 
 class FusionNet(nn.Module):
@@ -148,11 +148,13 @@ class FusionNet(nn.Module):
             merged = torch.empty(xa.shape[:2] + (fa + fs,), dtype=torch.float32, device=xa.device)
             cur = torch.cuda.current_stream()
             if self._streams is None:
-                self._streams = (torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream())
-            sa, sb, sc = self._streams
+                # (higher stream priority for the towers was measured: no gain)
+                self._streams = tuple(torch.cuda.Stream() for _ in range(4))
+            sa, sb, sc, sd = self._streams
             B = xa.shape[0]
             work = []
-            if B >= 2 * SPLIT_MIN_HALF and os.environ.get("GR_TOWER_SPLIT", "1") == "1":
+            split = os.environ.get("GR_TOWER_SPLIT", "2")
+            if B >= 2 * SPLIT_MIN_HALF and split in ("1", "2"):
                 # The speech recurrence of a 256-sequence batch holds 128 SMs (2 directions x 2 batch tiles x 32
                 # unit slices, one CTA per SM), so the skeletal recurrence (76 CTAs) cannot run beside it.  Two
                 # half-batch speech towers (64 CTAs each) can each share the GPU with it: 55.0 -> 52.8 ms/step.
@@ -161,9 +163,19 @@ class FusionNet(nn.Module):
 
                 def half(lo, hi):
                     return {k: (v[lo:hi] if k == "noise" else v[:, lo:hi].contiguous()) for k, v in sp.items()}
-                work = [(sa, lambda: self.speech.tower(xa[:h], half(0, h), merged[:h], 0)),
-                        (sb, lambda: self.skeletal.tower(xs, reg.get("sk"), merged, fa)),
-                        (sc, lambda: self.speech.tower(xa[h:], half(h, B), merged[h:], 0))]
+                sk = reg.get("sk") or {}
+
+                def half_sk(lo, hi):
+                    return {k: (v[lo:hi] if k == "noise" else v[:, lo:hi].contiguous()) for k, v in sk.items()}
+                if split == "2":   # the skeletal tower in halves as well (38 CTAs each): 51.3 -> 49.2 ms/step
+                    work = [(sa, lambda: self.speech.tower(xa[:h], half(0, h), merged[:h], 0)),
+                            (sb, lambda: self.skeletal.tower(xs[:h], half_sk(0, h), merged[:h], fa)),
+                            (sc, lambda: self.speech.tower(xa[h:], half(h, B), merged[h:], 0)),
+                            (sd, lambda: self.skeletal.tower(xs[h:], half_sk(h, B), merged[h:], fa))]
+                else:
+                    work = [(sa, lambda: self.speech.tower(xa[:h], half(0, h), merged[:h], 0)),
+                            (sb, lambda: self.skeletal.tower(xs, reg.get("sk"), merged, fa)),
+                            (sc, lambda: self.speech.tower(xa[h:], half(h, B), merged[h:], 0))]
             else:
                 work = [(sa, lambda: self.speech.tower(xa, reg.get("sp"), merged, 0)),
                         (sb, lambda: self.skeletal.tower(xs, reg.get("sk"), merged, fa))]

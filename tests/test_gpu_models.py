@@ -89,6 +89,7 @@ def test_half_batch_speech_towers_match_whole_batch(cuda, monkeypatch):
     independent; only the MMA row a sequence sits in changes)."""
     import mgr_b200 as mgr
     B, T = 128, 24
+    monkeypatch.setattr(mgr.models, "SPLIT_MIN_HALF", 64)
     sp, sk, fu = _small_nets(mgr, cuda, Ha=64, Hs=48)
     g = torch.Generator().manual_seed(5)
     xa = torch.randn(B, T, 39, generator=g).to(cuda)
@@ -99,7 +100,11 @@ def test_half_batch_speech_towers_match_whole_batch(cuda, monkeypatch):
     monkeypatch.setenv("GR_TOWER_SPLIT", "1")
     split = fu.merged(xa, xs, reg).clone()
     torch.cuda.synchronize()
+    monkeypatch.setenv("GR_TOWER_SPLIT", "2")
+    split2 = fu.merged(xa, xs, reg).clone()
+    torch.cuda.synchronize()
     assert (whole - split).abs().max().item() <= 1e-5
+    assert (whole - split2).abs().max().item() <= 1e-5
     assert whole.abs().max().item() > 1e-3
 
 
