@@ -1,0 +1,137 @@
+"""Keras-layout persistence for the three networks: `to_json` / `model_from_json` and
+`save_weights` / `load_weights`, mirroring what the reference does around training
+(`model.to_json()` + `model.save_weights(...)` in DataGenerator.on_epoch_end,
+/root/reference/audio_network/data_generator.py:277-281; `model_from_json` + `load_weights` of the two
+towers, /root/reference/multimodal_fusion/multimodal.py:68-85) and the tower re-use
+`speech_model.layers[2](x)`, `.layers[3](...)` (`multimodal.py:109-118`).
+
+Weights travel in KERAS ORDER -- per layer in `model.layers` order, per layer in `layer.weights` order,
+i.e. for `Bidirectional(LSTM)`: forward kernel (F,4H), forward recurrent kernel (H,4H), forward bias (4H),
+then the backward three; gate order i,f,c,o; for `Dense`: kernel, bias -- under the names Keras 2.1.4
+gives them (`bidirectional_1/forward_blstm_1/kernel:0`, ...), which is also how `load_weights` matches:
+by position, names are informative (Keras' topological loading).
+
+Container: `.npz` (NumPy).  The reference's `.h5` files are HDF5; h5py is not part of this image and an
+HDF5 reader that could not be checked against a single real Keras file would be guesswork, so the bridge
+is a ten-line conversion on any machine that has h5py: it walks
+`f.attrs['layer_names']` / `g.attrs['weight_names']` and writes the arrays in that order into the `.npz`
+this module reads.
+"""
+import json
+from collections import OrderedDict
+
+import numpy as np
+
+from .models import UnimodalNet, FusionNet
+
+_BLSTM_PARTS = ("kernel:0", "recurrent_kernel:0", "bias:0")
+
+
+def _blstm_entries(wrapper_name, lstm_name, layer):
+    w = layer.get_weights()
+    out = []
+    for d, direction in enumerate(("forward", "backward")):
+        for k, part in enumerate(_BLSTM_PARTS):
+            out.append(("%s/%s_%s/%s" % (wrapper_name, direction, lstm_name, part), w[3 * d + k]))
+    return out
+
+
+def weight_table(model, prefix=""):
+    """OrderedDict layer name -> [(weight name, array)] in Keras saving order."""
+    t = OrderedDict()
+    if isinstance(model, UnimodalNet):
+        t[prefix + "bidirectional_1"] = _blstm_entries(prefix + "bidirectional_1", "blstm_1", model.blstm_1)
+        t[prefix + "bidirectional_2"] = _blstm_entries(prefix + "bidirectional_2", "blstm_2", model.blstm_2)
+        d = model.dense.get_weights()
+        t[prefix + "dense_1"] = [(prefix + "dense_1/kernel:0", d[0]), (prefix + "dense_1/bias:0", d[1])]
+        return t
+    if isinstance(model, FusionNet):
+        # multimodal.py builds: speech layers[2], layers[3], skeletal layers[2], layers[3], new BLSTM(100), Dense
+        for name, tower in (("speech/", model.speech), ("skeletal/", model.skeletal)):
+            sub = weight_table(tower, prefix=name)
+            sub.pop(name + "dense_1")          # the uni-modal heads are not part of the fusion graph
+            t.update(sub)
+        t["bidirectional_3"] = _blstm_entries("bidirectional_3", "blstm_2", model.blstm_3)
+        d = model.dense.get_weights()
+        t["dense_1"] = [("dense_1/kernel:0", d[0]), ("dense_1/bias:0", d[1])]
+        return t
+    raise TypeError("weight_table: unsupported model %r" % type(model))
+
+
+def _assign(model, arrays):
+    """Inverse of weight_table's flattening: consume `arrays` in Keras order."""
+    it = iter(arrays)
+
+    def take(n):
+        return [next(it) for _ in range(n)]
+    if isinstance(model, UnimodalNet):
+        model.blstm_1.set_weights(take(6))
+        model.blstm_2.set_weights(take(6))
+        model.dense.set_weights(take(2))
+    else:
+        for tower in (model.speech, model.skeletal):
+            tower.blstm_1.set_weights(take(6))
+            tower.blstm_2.set_weights(take(6))
+        model.blstm_3.set_weights(take(6))
+        model.dense.set_weights(take(2))
+    rest = list(it)
+    if rest:
+        raise ValueError("load_weights: %d arrays left over" % len(rest))
+
+
+def save_weights(model, path):
+    """`model.save_weights(path)`: one array per Keras weight, keys 'NNN|<keras weight name>' (NNN keeps the order)."""
+    flat = [(n, a) for entries in weight_table(model).values() for n, a in entries]
+    np.savez(path, **{"%03d|%s" % (i, n): a for i, (n, a) in enumerate(flat)})
+    return [n for n, _ in flat]
+
+
+def load_weights(model, path):
+    """`model.load_weights(path)`: topological (positional) matching with shape checks, like Keras."""
+    with np.load(path) as z:
+        keys = sorted(z.files, key=lambda k: int(k.split("|", 1)[0]))
+        arrays = [z[k] for k in keys]
+    want = [a for entries in weight_table(model).values() for _, a in entries]
+    if len(arrays) != len(want):
+        raise ValueError("load_weights: file holds %d arrays, the model needs %d" % (len(arrays), len(want)))
+    for k, a, w in zip(keys, arrays, want):
+        if a.shape != w.shape:
+            raise ValueError("load_weights: %s has shape %s, the model expects %s" % (k, a.shape, w.shape))
+    _assign(model, arrays)
+    return keys
+
+
+def _unimodal_config(net):
+    return {"class_name": "UnimodalNet",
+            "config": {"numfeats": net.numfeats, "units": net.units, "nb_classes": net.nb_classes,
+                       "noise_std": net.noise_std, "dropouts": [net.p1, net.p2, net.pd]},
+            # what the reference's model.to_json() would describe (speech_lstm_ctc_words.py:46-90)
+            "keras_layers": ["InputLayer", "GaussianNoise", "Bidirectional(LSTM blstm_1)", "Bidirectional(LSTM blstm_2)",
+                             "Add", "Dropout", "Dense dense_1", "Activation softmax"]}
+
+
+def to_json(model):
+    """`model.to_json()`: the topology (not the weights) as a JSON string `model_from_json` rebuilds."""
+    if isinstance(model, UnimodalNet):
+        return json.dumps(_unimodal_config(model))
+    if isinstance(model, FusionNet):
+        return json.dumps({"class_name": "FusionNet",
+                           "config": {"nb_classes": model.nb_classes, "units": model.units,
+                                      "speech": _unimodal_config(model.speech),
+                                      "skeletal": _unimodal_config(model.skeletal)}})
+    raise TypeError("to_json: unsupported model %r" % type(model))
+
+
+def model_from_json(s):
+    """`keras.models.model_from_json`: rebuild the network (fresh initial weights; call load_weights next)."""
+    d = json.loads(s)
+
+    def uni(c):
+        c = c["config"]
+        return UnimodalNet(c["numfeats"], c["units"], c["nb_classes"], c["noise_std"], tuple(c["dropouts"]))
+    if d["class_name"] == "UnimodalNet":
+        return uni(d)
+    if d["class_name"] == "FusionNet":
+        c = d["config"]
+        return FusionNet(uni(c["speech"]), uni(c["skeletal"]), nb_classes=c["nb_classes"], units=c["units"])
+    raise ValueError("model_from_json: unknown class %r" % d["class_name"])
