@@ -1,0 +1,85 @@
+"""FusionTrainer bookkeeping (which towers are launched when, and which prefetch is trusted), on stub objects:
+no CUDA.  The numerical equivalence with the serial loop is a GPU test (tests/test_gpu_models.py)."""
+import numpy as np
+
+
+class _StubModel:
+    def __init__(self):
+        self.log = []
+
+    def sample_regularisers(self, B, T, seed, step, device):
+        self.log.append(("reg", step))
+        return {"step": step}
+
+    def launch_towers(self, xa, xs, reg, ready=None):
+        self.log.append(("towers", reg["step"], id(xa), ready))
+        return {"merged": None, "events": [], "inputs": (xa, xs)}
+
+    def loss_and_grads(self, xa, xs, labels, il, ll, reg, global_batch=None, towers=None):
+        assert towers["inputs"][0] is xa and towers["inputs"][1] is xs      # never someone else's features
+        self.log.append(("fusion", reg["step"], id(xa)))
+        return np.float32(reg["step"]), ["g%d" % reg["step"]]
+
+
+class _StubOpt:
+    def __init__(self):
+        self.seen = []
+
+    def step(self, grads):
+        self.seen.append(grads)
+
+
+class _T:
+    """stands in for a (B, T, F) tensor"""
+    shape = (4, 10, 3)
+    device = "cpu"
+
+
+def _trainer(hook=None):
+    import mgr_b200 as mgr
+    m, o = _StubModel(), _StubOpt()
+    return mgr.FusionTrainer(m, o, seed=5, global_batch=8, grad_hook=hook), m, o
+
+
+def test_serial_steps_launch_their_own_towers():
+    t, m, o = _trainer()
+    a, b = (_T(), _T()), (_T(), _T())
+    assert t.step(a + (0, 0, 0)) == 0 and t.step(b + (0, 0, 0)) == 1
+    assert [e[:2] for e in m.log] == [("reg", 0), ("towers", 0), ("fusion", 0), ("reg", 1), ("towers", 1), ("fusion", 1)]
+    assert o.seen == [["g0"], ["g1"]]
+
+
+def test_next_batch_towers_are_enqueued_before_this_batch_trains_and_reused():
+    t, m, _ = _trainer()
+    a, b, c = (_T(), _T()), (_T(), _T()), (_T(), _T())
+    t.step(a + (0, 0, 0), next_inputs=b, next_ready="ev1")
+    kinds = [e[:2] for e in m.log]
+    assert kinds == [("reg", 0), ("towers", 0), ("reg", 1), ("towers", 1), ("fusion", 0)]
+    assert m.log[3][3] == "ev1"                       # the copy event reaches launch_towers
+    m.log.clear()
+    t.step(b + (0, 0, 0), next_inputs=c)
+    assert [e[:2] for e in m.log] == [("reg", 2), ("towers", 2), ("fusion", 1)]   # batch b's towers were NOT relaunched
+    m.log.clear()
+    t.step(c + (0, 0, 0))                             # last batch: nothing to prefetch
+    assert [e[:2] for e in m.log] == [("fusion", 2)]
+
+
+def test_prefetch_for_other_tensors_is_discarded():
+    t, m, _ = _trainer()
+    a, b, other = (_T(), _T()), (_T(), _T()), (_T(), _T())
+    t.step(a + (0, 0, 0), next_inputs=b)
+    m.log.clear()
+    t.step(other + (0, 0, 0))                         # the caller changed its mind: same step index, other tensors
+    assert [e[:2] for e in m.log] == [("reg", 1), ("towers", 1), ("fusion", 1)]
+    assert m.log[1][2] == id(other[0])
+
+
+def test_grad_hook_sits_between_backward_and_optimiser():
+    calls = []
+
+    def hook(grads):
+        calls.append(list(grads))
+        return ["reduced"]
+    t, _, o = _trainer(hook)
+    t.step((_T(), _T(), 0, 0, 0))
+    assert calls == [["g0"]] and o.seen == [["reduced"]]
