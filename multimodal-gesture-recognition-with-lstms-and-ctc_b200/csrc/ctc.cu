@@ -917,6 +917,10 @@ static int launch_ctc(const CtcParams& p, cudaStream_t stream) {
     if (per_cta * need_per_sm <= smem_budget && per_cta <= 200 * 1024) break;
     TC >>= 1;
   }
+  if (const char* tcs = getenv("GR_CTC_TC")) {   // tests: force a smaller chunk than the batch size would pick
+    const int v = atoi(tcs);
+    if ((v == 8 || v == 16) && v < TC) TC = v;
+  }
   const size_t smem = ctc_smem_bytes_v4(p.C, p.Lmax, p.RS, TC);
   if (smem > 220 * 1024) return set_error(GR_EUNSUPPORTED, "ctc: C/Lmax too large for shared memory");
   auto go = [&](auto kern) -> int {

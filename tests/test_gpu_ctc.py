@@ -90,6 +90,32 @@ def test_chunk_boundaries_and_both_kernels(cuda, monkeypatch, impl, Tn):
     assert np.abs(grad2 - ref_g2).max() <= GRAD_TOL * np.abs(ref_g2).max()
 
 
+@pytest.mark.xfail(strict=False, reason="added after round 1's GPU budget was spent: the 16- and 8-frame chunk "
+                   "instantiations are only picked for very large batches and have not run on a GPU yet")
+@pytest.mark.parametrize("tc", ["16", "8"])
+def test_small_chunk_instantiations(cuda, monkeypatch, tc):
+    """The chunk size is chosen from the batch size (shared memory for a single wave); small test batches always
+    get 32 frames, so force the other two template instantiations (GR_CTC_TC)."""
+    import mgr_b200 as mgr
+    from oracle import ctc_ref
+    monkeypatch.setenv("GR_CTC_TC", tc)
+    B, T, C, Lmax = 3, 77, 22, 12
+    rng = np.random.default_rng(int(tc))
+    p, a = random_probs(rng, B, T, C)
+    il = np.array([[T - 2], [41], [17]])
+    labels, ll = random_labels(rng, B, Lmax, C, T_avail=il[:, 0])
+    loss, grad = _run(mgr, cuda, p, labels, il, ll)
+    ref_loss, ref_g = ctc_ref.ctc_lambda_func((p, labels, il, ll), want_grad=True)
+    assert np.abs(loss - ref_loss).max() <= LOSS_RTOL * np.abs(ref_loss).max()
+    ref_g = ref_g / B
+    scale = np.abs(ref_g).max(axis=2, keepdims=True) + 1e-12
+    assert (np.abs(grad - ref_g) / scale).max() <= GRAD_TOL
+    loss2, grad2 = _run(mgr, cuda, None, labels, il, ll, logits=a)
+    ref_loss2, ref_g2 = ctc_ref.softmax_ctc_grad_logits(a, labels, il, ll)
+    assert np.abs(loss2 - ref_loss2).max() <= LOSS_RTOL * np.abs(ref_loss2).max()
+    assert np.abs(grad2 - ref_g2).max() <= GRAD_TOL * np.abs(ref_g2).max()
+
+
 def test_edge_cases(cuda):
     import mgr_b200 as mgr
     from oracle import ctc_ref
