@@ -31,12 +31,22 @@ LMAX = 35
 METRIC = "fusion BLSTM-CTC train seq/s"
 
 
-def read_traffic(kernel):
-    """dram bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/), or None."""
+def read_traffic_shape(kernel):
     path = os.path.join(ROOT, "profiles", "r01_traffic.json")
     try:
         d = json.load(open(path)).get(kernel)
-        return None if d is None else {"dram_bytes": d["dram_bytes"], "shape": d["shape"], "source": "profiles/r01_traffic.json"}
+        return None if d is None else "%s (profiles/r01_traffic.json)" % d["shape"]
+    except Exception:
+        return None
+
+
+def read_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full`
+    capture (profiles/r01_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        d = json.load(open(path)).get(kernel)
+        return None if d is None else d["dram_bytes"]
     except Exception:
         return None
 
@@ -217,6 +227,7 @@ def ctc_microbench(dev, peak_gbs):
             "frames_per_s": frames / (ms * 1e-3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                          "frac": achieved / peak_gbs, "traffic": read_traffic("gr_ctc_loss_grad_f32"),
+                         "traffic_capture": read_traffic_shape("gr_ctc_loss_grad_f32"),
                          "algorithmic_bytes_per_frame": bytes_per_frame}}
 
 
@@ -421,7 +432,8 @@ def run_gpu(args):
         avg_ms = per_kernel[dom]["avg_ms"]
         ach = tot_bytes / (avg_ms * 1e-3) / 1e9
         roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": read_traffic(dom), "peak_kind": peak_kind,
+                    "frac": ach / hbm_peak, "traffic": read_traffic(dom), "traffic_capture": read_traffic_shape(dom),
+                    "peak_kind": peak_kind,
                     "avg_launch_ms": avg_ms, "share_of_step": per_kernel[dom]["ms_per_step"] / serial_ms,
                     "serial_step_ms": serial_ms,
                     "note": "durations from serial steps run right after the timed region (kernel alone on the GPU); "
@@ -433,7 +445,8 @@ def run_gpu(args):
         avg_ms = per_kernel[dom]["avg_ms"]
         ach = flops / (avg_ms * 1e-3) / 1e12
         roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s",
-                    "frac": ach / tc_peak, "traffic": read_traffic(dom), "peak_kind": peak_kind, "avg_launch_ms": avg_ms,
+                    "frac": ach / tc_peak, "traffic": read_traffic(dom), "traffic_capture": read_traffic_shape(dom),
+                    "peak_kind": peak_kind, "avg_launch_ms": avg_ms,
                     "share_of_step": per_kernel[dom]["ms_per_step"] / serial_ms, "serial_step_ms": serial_ms,
                     "note": "durations from serial steps run right after the timed region; algorithmic flops 2MNK "
                             "(bf16x3 executes 3x that on the tensor pipe)"}
