@@ -231,6 +231,44 @@ def ctc_microbench(dev, peak_gbs):
                          "algorithmic_bytes_per_frame": bytes_per_frame}}
 
 
+def ctc_sweep(dev, peak_gbs):
+    """BASELINE config 4 as written: B=1024, T in {100..2000}, L in {1,10,20,40} (capped at T/2), C=22, full and
+    ragged input lengths.  Opt-in (`--ctc-sweep`): ~60 kernel shapes."""
+    import torch
+    from mgr_b200 import ops
+    B, C = 1024, 22
+    out = []
+    rng = np.random.default_rng(3002)
+    for T in (100, 200, 400, 800, 1000, 1600, 2000):
+        g = torch.Generator().manual_seed(3001 + T)
+        probs = torch.softmax(torch.randn(B, T + 2, C, generator=g) * 2, -1).to(dev)
+        for L in (1, 10, 20, 40):
+            L = min(L, T // 2)
+            labels = torch.tensor(rng.integers(0, C - 1, size=(B, L)), dtype=torch.int32, device=dev)
+            ll = torch.full((B,), L, dtype=torch.int32, device=dev)
+            for ragged in (False, True):
+                il_np = rng.integers(max(T // 2, L), T + 1, size=B) if ragged else np.full(B, T)
+                il = torch.tensor(il_np, dtype=torch.int32, device=dev)
+                for _ in range(2):
+                    ops.ctc_loss_grad(probs, labels, ll, il, False)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n = 5
+                e0.record()
+                for _ in range(n):
+                    ops.ctc_loss_grad(probs, labels, ll, il, False)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / n
+                frames = int(il_np.sum())
+                bpf = 8 * C + 8 * (2 * L + 1)
+                ach = frames * bpf / (ms * 1e-3) / 1e9
+                out.append({"T": T, "L": L, "ragged": ragged, "ms": ms, "frames_per_s": frames / (ms * 1e-3),
+                            "achieved_GBps": ach, "frac": ach / peak_gbs})
+        del probs
+    return out
+
+
 def decode_microbench(dev, peak_gbs):
     """BASELINE config 5: N=512, T=1000, C=22 'peaky' probabilities; thresholded best path
     (sequence_decoding.py semantics), TF greedy and beam-width-100 decode.  CUDA events."""
@@ -451,6 +489,8 @@ def run_gpu(args):
                     "note": "durations from serial steps run right after the timed region; algorithmic flops 2MNK "
                             "(bf16x3 executes 3x that on the tensor pipe)"}
     ctc = ctc_microbench(dev, hbm_peak) if not args.skip_ctc else None
+    if ctc is not None and args.ctc_sweep:
+        ctc["sweep"] = ctc_sweep(dev, hbm_peak)
     decode = decode_microbench(dev, hbm_peak) if not args.skip_ctc else None
     cpu = None
     if not args.skip_cpu:
@@ -507,6 +547,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=32, help="sequences per CPU-baseline step (bounded sample)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-ctc", action="store_true")
+    ap.add_argument("--ctc-sweep", action="store_true", help="add the full BASELINE config-4 sweep to the 'ctc' object")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
     ap.add_argument("--min-warmup", type=int, default=3, help="profiling runs only (ncu launch lists)")
     args = ap.parse_args()
