@@ -348,7 +348,10 @@ def run_gpu(args):
     # spin on each other) share the GPU with the NCCL all-reduce of step n; N=2 ran clean with it twice (10.7k seq/s)
     # but one N=2 run and the only N=4 run of round 1 did not finish, so until that is understood the data-parallel
     # runs use the strictly serial step that rounds of N=2/N=4 runs have validated.  GR_PIPELINE=1 forces it on.
-    pipeline = os.environ.get("GR_PIPELINE", "1" if world == 1 else "0") == "1"
+    # GR_PIPELINE=2: pipeline on, but the all-reduce waits for the prefetched towers (candidate fix, not yet run).
+    pmode = os.environ.get("GR_PIPELINE", "1" if world == 1 else "0")
+    pipeline = pmode in ("1", "2")
+    trainer.hook_after_towers = pmode == "2"
 
     def train_step(xa, xs, lab, il, ll, nxt=None, nxt_ready=None):
         return trainer.step((xa, xs, lab, il, ll), next_inputs=nxt if pipeline else None, next_ready=nxt_ready)

@@ -270,9 +270,12 @@ class FusionTrainer:
         loss = trainer.step(batch_n, next_inputs=(xa_next, xs_next))     # batch = (xa, xs, labels, il, ll)
     """
 
-    def __init__(self, model, opt, seed=0, global_batch=None, grad_hook=None):
+    def __init__(self, model, opt, seed=0, global_batch=None, grad_hook=None, hook_after_towers=False):
         self.model, self.opt, self.seed, self.global_batch = model, opt, seed, global_batch
         self.grad_hook = grad_hook        # e.g. pack + all-reduce of the flat gradient bucket (data parallel)
+        # True: the calling stream waits for the prefetched towers before the hook runs, so that a collective in
+        # the hook never shares the GPU with the (cooperatively launched) recurrence kernels -- DESIGN 5
+        self.hook_after_towers = hook_after_towers
         self.step_no = 0                  # next step to be trained
         self._pending = None              # (step index, reg, towers handle)
 
@@ -296,6 +299,8 @@ class FusionTrainer:
         loss, grads = self.model.loss_and_grads(xa, xs, labels, il, ll, reg, global_batch=self.global_batch,
                                                 towers=towers)
         if self.grad_hook is not None:
+            if self.hook_after_towers and self._pending is not None:
+                self.model.join_towers(self._pending[2])
             grads = self.grad_hook(grads)
         self.opt.step(grads)
         self.step_no += 1

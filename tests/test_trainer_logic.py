@@ -15,6 +15,10 @@ class _StubModel:
         self.log.append(("towers", reg["step"], id(xa), ready))
         return {"merged": None, "events": [], "inputs": (xa, xs)}
 
+    def join_towers(self, handle):
+        self.log.append(("join", id(handle["inputs"][0])))
+        return handle["merged"]
+
     def loss_and_grads(self, xa, xs, labels, il, ll, reg, global_batch=None, towers=None):
         assert towers["inputs"][0] is xa and towers["inputs"][1] is xs      # never someone else's features
         self.log.append(("fusion", reg["step"], id(xa)))
@@ -83,3 +87,14 @@ def test_grad_hook_sits_between_backward_and_optimiser():
     t, _, o = _trainer(hook)
     t.step((_T(), _T(), 0, 0, 0))
     assert calls == [["g0"]] and o.seen == [["reduced"]]
+
+
+def test_hook_can_be_ordered_after_the_prefetched_towers():
+    order = []
+    t, m, _ = _trainer(lambda g: order.append(("hook", len(m.log))) or g)
+    t.hook_after_towers = True
+    a, b = (_T(), _T()), (_T(), _T())
+    t.step(a + (0, 0, 0), next_inputs=b)
+    joins = [i for i, e in enumerate(m.log) if e[0] == "join"]
+    assert joins and m.log[joins[-1]][1] == id(b[0])          # the calling stream joined batch b's towers ...
+    assert order[0][1] == joins[-1] + 1                        # ... right before the hook ran
