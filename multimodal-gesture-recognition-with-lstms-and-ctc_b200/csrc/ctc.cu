@@ -1,7 +1,7 @@
 // CTC loss + gradient for sm_100a.  Replaces ctc_lambda_func -> K.ctc_batch_cost -> tf.nn.ctc_loss
 // (/root/reference/audio_network/losses.py:4-15; TF CTCLossCalculator semantics).
 //
-// Design (DESIGN.md "K6"): one CTA of two warps per sequence.  Warp 0 runs the alpha recursion
+// Design: one CTA of two warps per sequence.  Warp 0 runs the alpha recursion
 // forward in time; warp 1 runs the SAME recursion on the time-reversed, label-reversed problem,
 // which is the beta recursion with the emission folded in (gamma = beta + log y).  They meet at
 // t* = Tn/2: log p = logsumexp_u(alpha + gamma - log y)(t*).  Each warp then keeps going through
