@@ -137,3 +137,38 @@ def test_to_device_argument_order(tmp_path):
     xa, xs, lab, il, ll = to_device(inp, torch.device("cpu"), pinned=False)
     assert xa.shape == (2, 20, 39) and xs.shape == (2, 20, 20) and lab.shape == (2, 35)
     assert il.dtype == torch.int64 and ll.dtype == torch.int64 and xa.dtype == torch.float32
+
+
+def test_generators_agree_on_random_configurations(tmp_path):
+    """Random mini-batch sizes, split fractions, sequence lengths and dataset sizes (seeded sweep rather than
+    hypothesis: each case writes a small dataset to disk)."""
+    from mgr_b200.data_generator import AudioDataGenerator, FusionDataGenerator
+    from oracle import data_ref
+    rng = np.random.default_rng(11)
+    for case in range(4):
+        root = tmp_path / ("case%d" % case)
+        os.makedirs(root)
+        n_files = int(rng.integers(7, 19))
+        ids = sorted(rng.choice(np.arange(1, 400), size=n_files, replace=False).tolist())
+        blank = tuple(rng.choice(ids, size=2, replace=False).tolist())
+        _write_dataset(str(root), "train", ids, rng, blank_ids=blank, no_skeletal=(ids[0],), long_ids=(ids[-1],))
+        mb = int(rng.integers(1, 5))
+        vs = float(rng.choice([0.1, 0.2, 0.34, 0.5]))
+        maxlen = int(rng.integers(8, 40))
+        a_args = dict(minibatch_size=mb, numfeats=39, maxlen=maxlen, nb_classes=44, dataset="train", val_split=vs,
+                      absolute_max_sequence_len=60, data_root=str(root))
+        f_args = dict(minibatch_size=mb, numfeats_skeletal=20, numfeats_speech=39, maxlen=maxlen, nb_classes=22,
+                      dataset="train", val_split=vs, absolute_max_sequence_len=35, data_root=str(root))
+        for g, r in ((AudioDataGenerator(**a_args), data_ref.AudioGeneratorRef(**a_args)),
+                     (FusionDataGenerator(**f_args), data_ref.FusionGeneratorRef(**f_args))):
+            assert g.get_file_list(True) == r.train_list and g.get_file_list(False) == r.val_list
+            for train in (True, False):
+                if g.get_size(train) == 0:
+                    continue
+                n = g.get_size(train) // mb + 1
+                it = g.next_train() if train else g.next_val()
+                for (gi, _), (ri, _) in zip((next(it) for _ in range(n)), data_ref.next_batches(r, train, n)):
+                    _same(gi, ri)
+            g.on_epoch_end()
+            data_ref.on_epoch_end(r)
+            assert g.get_file_list(True) == r.train_list and g.get_file_list(False) == r.val_list
