@@ -90,8 +90,10 @@ def test_chunk_boundaries_and_both_kernels(cuda, monkeypatch, impl, Tn):
     assert np.abs(grad2 - ref_g2).max() <= GRAD_TOL * np.abs(ref_g2).max()
 
 
-@pytest.mark.xfail(strict=False, reason="added after round 1's GPU budget was spent: the 16- and 8-frame chunk "
-                   "instantiations are only picked for very large batches and have not run on a GPU yet")
+@pytest.mark.skipif(__import__("os").environ.get("GR_RUN_UNVERIFIED") != "1",
+                    reason="added after round 1's GPU budget was spent: the 16- and 8-frame chunk instantiations (only "
+                           "picked for very large batches) have not run on a GPU yet; a fault in an unverified kernel "
+                           "would poison the CUDA context for the rest of the suite, so it runs on request only")
 @pytest.mark.parametrize("tc", ["16", "8"])
 def test_small_chunk_instantiations(cuda, monkeypatch, tc):
     """The chunk size is chosen from the batch size (shared memory for a single wave); small test batches always
