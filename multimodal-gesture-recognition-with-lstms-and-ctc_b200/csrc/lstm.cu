@@ -282,16 +282,28 @@ size_t lstm_tc_trace_offset(int B, int H);
 int lstm_fwd_tc_launch(float* gates, const float* U, int B, int T, int H, float* y, float* cell, void* workspace,
                        cudaStream_t s);
 
+// tensor-core forward path with U resident in tensor memory (lstm_tcu.cu)
+bool lstm_tcu_supported(int B, int H);
+size_t lstm_tcu_workspace_bytes(int B, int H);
+size_t lstm_tcu_trace_offset(int B, int H);
+int lstm_fwd_tcu_launch(float* gates, const float* U, int B, int T, int H, float* y, float* cell, void* workspace,
+                        cudaStream_t s);
+
 // register-resident-U path for narrow layers (lstm_small.cu)
 bool lstm_small_supported(int H);
 int lstm_small_run(bool bwd, float* gates, const float* U, int B, int T, int H, float* y, float* cell,
                    const float* dy, cudaStream_t s);
 
-// GR_LSTM_IMPL = generic | tc | small forces one implementation (debugging / cross-checks)
+// GR_LSTM_IMPL = generic | tc | tcu | small forces one implementation (debugging / cross-checks)
 static bool use_small_path(int H) {
   const char* e = getenv("GR_LSTM_IMPL");
   if (e && strcmp(e, "small") != 0) return false;
   return lstm_small_supported(H);
+}
+static bool use_tcu_path(int B, int H) {
+  const char* e = getenv("GR_LSTM_IMPL");
+  if (!e || strcmp(e, "tcu") != 0) return false;   // opt-in until it has passed the GPU parity tests
+  return lstm_tcu_supported(B, H);
 }
 static bool use_tc_path(int B, int H) {
   const char* e = getenv("GR_LSTM_IMPL");
@@ -311,6 +323,7 @@ static void lstm_config(int B, int H, int* HS, int* UG, int* Bp) {
 }  // namespace gr
 
 extern "C" size_t gr_debug_lstm_tc_trace_offset(int B, int H) { return gr::lstm_tc_trace_offset(B, H); }
+extern "C" size_t gr_debug_lstm_tcu_trace_offset(int B, int H) { return gr::lstm_tcu_trace_offset(B, H); }
 
 extern "C" int gr_lstm_workspace_bytes(int B, int H, size_t* bytes_out) {
   if (B <= 0 || H <= 0 || !bytes_out) return gr::set_error(GR_EINVAL, "lstm_workspace_bytes: bad argument");
@@ -318,6 +331,8 @@ extern "C" int gr_lstm_workspace_bytes(int B, int H, size_t* bytes_out) {
   // counters (256 B) + dG^T exchange (2*2*4H*Bp) [the h^T exchange aliases it] + carried state (2*B*H)
   size_t generic = 256 + sizeof(float) * ((size_t)16 * H * Bp + (size_t)2 * B * H) + 256;
   size_t tc = gr::lstm_tc_supported(B, H) ? gr::lstm_tc_workspace_bytes(B, H) : 0;
+  size_t tcu = gr::lstm_tcu_supported(B, H) ? gr::lstm_tcu_workspace_bytes(B, H) : 0;
+  if (tcu > tc) tc = tcu;
   *bytes_out = generic > tc ? generic : tc;
   return GR_OK;
 }
@@ -333,6 +348,8 @@ extern "C" int gr_lstm_recurrence_fwd_f32(float* gates, const float* U, int B, i
   if (workspace_bytes < need) return set_error(GR_EWORKSPACE, "lstm_fwd: workspace too small");
   if (use_small_path(H))
     return lstm_small_run(false, gates, U, B, T, H, y, cell, nullptr, static_cast<cudaStream_t>(stream));
+  if (use_tcu_path(B, H))
+    return lstm_fwd_tcu_launch(gates, U, B, T, H, y, cell, workspace, static_cast<cudaStream_t>(stream));
   if (use_tc_path(B, H))
     return lstm_fwd_tc_launch(gates, U, B, T, H, y, cell, workspace, static_cast<cudaStream_t>(stream));
   LstmFwdParams p;

@@ -1,0 +1,565 @@
+// Bidirectional Keras-LSTM forward recurrence, second tcgen05 design: the recurrent kernel U lives in TENSOR
+// MEMORY and the operands are swapped.  Replaces the tf.while_loop body behind
+// `Bidirectional(LSTM(H, tanh, hard_sigmoid))` (/root/reference/audio_network/speech_lstm_ctc_words.py:56-77,
+// skeletal_network/skeletal_lstm_ctc.py:309-331) for the wide layers (H = 300 / 500).
+//
+// What lstm_tc.cu (round 1) ran into: with U resident in shared memory (128 KB of bf16 hi/lo per 16 units) the
+// MMA phase sits at the shared-memory bandwidth floor (h tile written by TMA + read twice as the A operand +
+// the U tile read as B), only two or three 32 KB ring stages fit beside U, and a CTA can hold a single batch tile,
+// so the ~7000-cycle publish -> counter -> poll -> TMA chain between two steps is fully exposed.
+//
+// Here, per CTA = (direction, 16 hidden units, up to two batch tiles of NB rows):
+//   * A operand = this CTA's 64 gate columns of U as 128 M-rows (bf16 hi rows and lo rows), K-major in TMEM
+//     (<= 256 columns, written once with tcgen05.st); tcgen05.mma reads it from TMEM (TS form), so shared memory
+//     carries only the streamed h tiles: B operand = [NB batch rows x 64 k] K-major SWIZZLE_128B, N = NB.
+//     D[128 x NB] (fp32, TMEM) accumulates A x h_hi^T and A x h_lo^T:  rows 0..63 of a lane group hold
+//     U_hi (h_hi + h_lo), rows +8 hold U_lo (h_hi + h_lo); their sum is the bf16x3 product plus the (harmless)
+//     lo x lo term.
+//   * The freed shared memory holds a 4-stage 32 KB h ring and double-buffered P / y / c / gates staging, and the
+//     CTA interleaves TWO independent batch tiles: while tile 0's epilogue publishes h_t and the group's counter
+//     round trip runs, the tensor pipe works on tile 1 (and vice versa).
+//   * Epilogue: TMEM lane = gate row, column = batch row, so one unit's four gates (x hi/lo rows) sit in eight
+//     lanes of one 32-lane quadrant.  tcgen05.ld.32x32b hands thread l its row for 8X columns; a three-stage
+//     shuffle butterfly over the 8 threads that share a unit (lane bits 4,3,2) adds the hi and lo rows and turns
+//     "one gate row x 8X cells" into "four gates x X cells" per thread.  (tcgen05.ld.16x256b, whose fragment
+//     would save the first stage, was measured at ~300 cycles per 16-lane x 8-column atom: 5400 cycles per
+//     128-row tile.)
+//   * h_t is staged as fp32 in shared memory (the y tile that the IO warp stores with TMA anyway), converted to
+//     bf16 hi/lo by one thread per (row, part) and written to the L2 exchange buffer as whole 32-byte sectors.
+// Warp roles: 0 = h TMA (polls the step counter of the tile's group), 1 = MMA issue, 2..9 = epilogue,
+// 10 = IO (P loads, y / c / gates stores as 4-D TMA tensor copies), 11 idle.
+#include <stdlib.h>
+#include "tc_common.cuh"
+
+namespace gr {
+
+static constexpr int kUThreads = 384;
+static constexpr int kUEpi = 256;
+static constexpr int kUUnits = 16;
+static constexpr int kURing = 4;
+static constexpr uint32_t kUStage = 32768;
+static constexpr uint32_t kDBase = 256;   // first accumulator column; A occupies columns [0, 8*KS) <= 256
+
+struct LstmTcuParams {
+  uint8_t* hx;                 // exchange: [(K chunk, hi|lo) slab][(dir, parity, padded batch row)][64 bf16]
+  unsigned* counters;          // (dir, global tile) x 32 words
+  const __nv_bfloat16* ut_hi;  // (8H, Kp8): row = dir*4H + gate*H + unit, K-major
+  const __nv_bfloat16* ut_lo;
+  long long* trace;
+  int B, T, H, Bpad, UGn, NTg, NSB, Kc, KS, Kp8, CP, NREQ, save;
+  int dbg;                     // GR_TCU_DBG experiments: 1 = MMAs of the next tile are NOT held back behind the epilogue's tcgen05.ld
+};
+
+#define TCU_TRACE(slot, n) do { if (p.trace && (n) < 256) p.trace[((size_t)blockIdx.x * 256 + (n)) * 16 + (slot)] = clock64(); } while (0)
+
+__device__ __forceinline__ float hsig_u(float v) { return fminf(fmaxf(0.2f * v + 0.5f, 0.f), 1.f); }
+__device__ __forceinline__ float tanh_u(float x) {
+  const float e = ex2_approx(x * 2.8853900817779268f);
+  return 1.0f - __fdividef(2.0f, 1.0f + e);
+}
+__device__ __forceinline__ void tma_load_3d_u(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_u(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d_u(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ bool elect_one_u() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive_u(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// A operand from tensor memory (TS form)
+__device__ __forceinline__ void umma_ts_bf16(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ float fsel(bool c, float a, float b) {   // c ? a : b as one SEL
+  float r;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tselp.f32 %0, %1, %2, p;\n\t}" : "=f"(r) : "f"(a), "f"(b), "r"((uint32_t)c));
+  return r;
+}
+// byte offset of the 16-byte chunk `chunk` of row r inside a [rows][16 fp32] tile moved by TMA with SWIZZLE_64B
+__device__ __forceinline__ uint32_t sw64u(uint32_t r, uint32_t chunk) { return r * 64u + ((chunk ^ ((r >> 1) & 3u)) << 4); }
+
+// tcgen05.ld.32x32b.x8: register c <- (lane base + thread, column base + c)
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t* w) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "r"(taddr) : "memory");
+}
+
+// NB = batch rows per tile (16, 32, 64, 128); a CTA owns up to two tiles.
+template <int NB>
+__global__ void __launch_bounds__(kUThreads, 1)
+lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmG,
+                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmC, LstmTcuParams p) {
+  constexpr int X = NB / 16;                    // 8-column groups per epilogue warp (each warp: NB/2 columns)
+  constexpr uint32_t kIo = NB * 256;            // P / gates tile: [4 gates][NB rows][16 units] fp32
+  constexpr uint32_t kYs = NB * 64;             // y (and c) staging: [NB rows][16 units] fp32
+  constexpr uint32_t kSlot = kIo + 2 * kYs;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;                                   // kURing stages of <= 32 KB
+  uint8_t* slots = ring + (size_t)kURing * kUStage;       // 2 x { io, ystage, cstage }
+  uint64_t* full = reinterpret_cast<uint64_t*>(slots + 2 * kSlot);
+  uint64_t* empty = full + kURing;
+  uint64_t* tmem_full = empty + kURing;    // [2]  tile's MMAs of this step are complete
+  uint64_t* p_full = tmem_full + 2;        // [2]  P tile of the slot landed (implies: the slot's staging is free)
+  uint64_t* stage_ready = p_full + 2;      // [2]  256 epilogue threads staged the slot's outputs
+  uint64_t* ld_done = stage_ready + 2;     // 256 epilogue threads hold the tile's accumulator in registers
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(ld_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ug = blockIdx.x % p.UGn;
+  const int sb = (blockIdx.x / p.UGn) % p.NSB;
+  const int dir = blockIdx.x / (p.UGn * p.NSB);
+  const int j0 = ug * kUUnits;
+  const int H = p.H, T = p.T;
+  const int ntl = min(2, p.NTg - 2 * sb);               // tiles of this CTA
+  const uint32_t stage_bytes = (uint32_t)p.CP * 2u * NB * 128u;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmH)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmG)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
+    for (int s = 0; s < kURing; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&p_full[s], 1); mbar_init(&stage_ready[s], kUEpi); }
+    mbar_init(ld_done, kUEpi);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  // ---- one-time: U slice -> TMEM.  Lane L = 32q + 16 part + 4 gate + ul holds unit 4q + ul.
+  if (warp >= 2 && warp < 6) {
+    const int q = warp & 3;
+    const int part = lane >> 4, gate = (lane >> 2) & 3, ul = lane & 3;
+    const int unit = j0 + 4 * q + ul;
+    const __nv_bfloat16* src = (part ? p.ut_lo : p.ut_hi) + ((size_t)dir * 4 * H + (size_t)gate * H + unit) * p.Kp8;
+    const bool live = unit < H;
+    for (int ks = 0; ks < p.KS; ++ks) {
+      uint32_t w[8];
+#pragma unroll
+      for (int hseg = 0; hseg < 2; ++hseg) {
+        const int k0 = ks * 16 + hseg * 8;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (live && k0 < H) v = *reinterpret_cast<const uint4*>(src + k0);   // k0 + 8 <= Kp8 (H is a multiple of 4)
+        uint32_t e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int k = k0 + 2 * c;
+          if (k >= H) e[c] = 0u;
+          else if (k + 1 >= H) e[c] &= 0xffffu;
+          w[hseg * 4 + c] = e[c];
+        }
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ks * 8);
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                   ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  if (warp == 0) {
+    // ---- h stream: for every (step, tile) poll the tile group's counter, then NREQ tensor requests of
+    // [64 k][NB rows][2*CP slabs] (one elected lane issues; the loops stay warp-uniform)
+    int st = 0;
+    uint32_t ph = 0;
+    for (int s = 1; s < T; ++s) {
+      for (int tau = 0; tau < ntl; ++tau) {
+        const int gt = 2 * sb + tau;
+        const unsigned* ctr = p.counters + (dir * p.NTg + gt) * 32;
+        const unsigned target = (unsigned)s * p.UGn * 8u;   // 8 epilogue warps per CTA release once per step
+        unsigned v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        } while (v < target);
+        asm volatile("fence.proxy.async;" ::: "memory");
+        if (lane == 0) TCU_TRACE(0, s * ntl + tau);
+        const int row = (dir * 2 + ((s + 1) & 1)) * p.Bpad + gt * NB;
+        for (int r = 0; r < p.NREQ; ++r) {
+          mbar_wait(&empty[st], ph ^ 1);
+          if (elect_one_u()) {
+            mbar_expect_tx(&full[st], stage_bytes);
+            tma_load_3d_u(ring + (size_t)st * kUStage, &tmH, &full[st], 0, row, 2 * p.CP * r);
+          }
+          __syncwarp();
+          if (++st == kURing) { st = 0; ph ^= 1; }
+        }
+        if (lane == 0) TCU_TRACE(1, s * ntl + tau);
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issue: D[tile] (128 x NB, fp32) = sum_k A[:, k] (TMEM) x (h_hi + h_lo)[tile rows, k]^T
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int st = 0;
+    uint32_t ph = 0;
+    for (int s = 1; s < T; ++s) {
+      for (int tau = 0; tau < ntl; ++tau) {
+        const uint32_t dcol = tmem_base + kDBase + (uint32_t)(tau * NB);
+        // A tcgen05.ld issued while MMAs are queued is served behind them (measured: the epilogue's two loads took
+        // ~5400 cycles = the other tile's whole MMA phase), so this tile's MMAs are not issued before the epilogue
+        // has the previous tile's accumulator in registers; the rest of that epilogue overlaps with them.
+        const int m = (s - 1) * ntl + tau;
+        if (m > 0 && !(p.dbg & 1)) mbar_wait(ld_done, (uint32_t)((m - 1) & 1));
+        for (int r = 0; r < p.NREQ; ++r) {
+          mbar_wait(&full[st], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (lane == 0 && r == 0) TCU_TRACE(2, s * ntl + tau);
+          const uint32_t sa = smem_u32(ring + (size_t)st * kUStage);
+          if (elect_one_u()) {
+            for (int cc = 0; cc < p.CP; ++cc) {
+              const int c = r * p.CP + cc;
+              if (c >= p.Kc) break;
+              const uint64_t dBh = make_sw128_desc(sa + (uint32_t)(cc * 2) * (NB * 128u));
+              const uint64_t dBl = make_sw128_desc(sa + (uint32_t)(cc * 2 + 1) * (NB * 128u));
+              const int nk = min(4, p.KS - 4 * c);
+              for (int k = 0; k < nk; ++k) {
+                const uint32_t a = tmem_base + (uint32_t)((4 * c + k) * 8);
+                umma_ts_bf16(dcol, a, dBh + (uint64_t)(k * 2), idesc, (c > 0 || k > 0) ? 1u : 0u);
+                umma_ts_bf16(dcol, a, dBl + (uint64_t)(k * 2), idesc, 1u);
+              }
+            }
+            umma_commit(&empty[st]);
+          }
+          __syncwarp();
+          if (++st == kURing) { st = 0; ph ^= 1; }
+        }
+        if (elect_one_u()) umma_commit(&tmem_full[tau]);
+        __syncwarp();
+        if (lane == 0) TCU_TRACE(3, s * ntl + tau);
+      }
+    }
+  } else if (warp < 10) {
+    // ---- epilogue.  Warp w may touch TMEM lanes 32*(w%4)..+31 (units 4q..4q+3); warps w and w+4 split the
+    // tile's columns.  Thread l: row part = l>>4, gate gam = (l>>2)&3, unit 4q + (l&3).
+    const int q = warp & 3;
+    const int hw = (warp - 2) >> 2;
+    const int part = lane >> 4, gam = (lane >> 2) & 3, ul = lane & 3;
+    const int et = threadIdx.x - 64;                 // 0..255
+    // after the butterfly this thread owns the cells (unit 4q + ul, column hw*NB/2 + 8*mm + 4*part + gam), mm < X:
+    // the 32 lanes of one access then touch 8 consecutive rows x 4 consecutive words = 32 different banks
+    const uint32_t uword = (uint32_t)ul * 4u;
+    uint32_t coff[X];     // byte offset of the cell inside a [NB rows][16 units] SWIZZLE_64B tile
+#pragma unroll
+    for (int mm = 0; mm < X; ++mm) {
+      const uint32_t col = (uint32_t)(hw * (NB / 2) + 8 * mm + 4 * part + gam);
+      coff[mm] = sw64u(col, (uint32_t)q) + uword;
+    }
+    // publisher role: thread et < 2*NB converts row et>>1, part et&1 of the staged y tile
+    const int prow = et >> 1, ppart = et & 1;
+    const size_t R = (size_t)4 * p.Bpad;
+    float c_state[2][X];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int mm = 0; mm < X; ++mm) c_state[a][mm] = 0.f;
+
+    for (int s = 0; s < T; ++s) {
+#pragma unroll
+      for (int tau = 0; tau < 2; ++tau) {
+        if (tau >= ntl) break;
+        const int n = s * ntl + tau;
+        const int slot = n & 1;
+        const uint32_t sph = (uint32_t)(n >> 1) & 1u;
+        uint8_t* io = slots + (size_t)slot * kSlot;
+        uint8_t* ystage = io + kIo;
+        uint8_t* cstage = ystage + kYs;
+        float pre[X][4];
+        if (et == 0) TCU_TRACE(11, n);
+        mbar_wait(&p_full[slot], sph);
+#pragma unroll
+        for (int mm = 0; mm < X; ++mm)
+#pragma unroll
+          for (int g = 0; g < 4; ++g) pre[mm][g] = *reinterpret_cast<const float*>(io + g * kYs + coff[mm]);
+        if (et == 0) TCU_TRACE(9, n);
+        if (s > 0) {
+          mbar_wait(&tmem_full[tau], (uint32_t)((s - 1) & 1));
+          if (et == 0) TCU_TRACE(4, n);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          uint32_t v[8 * X];          // this thread's row, columns hw*NB/2 + [0, 8X)
+          const uint32_t taddr = tmem_base + kDBase + (uint32_t)(tau * NB + hw * (NB / 2)) + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+          for (int j = 0; j < X; ++j) tmem_ld_32x8(taddr + (uint32_t)(8 * j), v + 8 * j);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (et == 0) TCU_TRACE(12, n);
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive_u(ld_done);
+          if (et == 0) TCU_TRACE(13, n);
+          // column 8*mm + k, k = 4 kp + 2 k1 + k0.  Stage 1 (lane ^ 16): keep kp == part, add the partner's row
+          // (same gate column, other bf16 part).  Stage 2 (lane ^ 8, gate bit 1): keep k1.  Stage 3 (lane ^ 4): keep k0.
+          const bool bp = part != 0, b1 = (gam & 2) != 0, b0 = (gam & 1) != 0;
+          float w4[4 * X];              // [mm][k1 k0]
+#pragma unroll
+          for (int mm = 0; mm < X; ++mm)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float keep = __uint_as_float(bp ? v[8 * mm + 4 + k] : v[8 * mm + k]);
+              const float send = __uint_as_float(bp ? v[8 * mm + k] : v[8 * mm + 4 + k]);
+              w4[4 * mm + k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+          if (et == 0) { asm volatile("" ::"f"(w4[0]), "f"(w4[4 * X - 1]) : "memory"); TCU_TRACE(14, n); }
+          float a0[2 * X], a1[2 * X];   // [mm][k0]: a0 = own gate gam, a1 = gate gam^2
+#pragma unroll
+          for (int mm = 0; mm < X; ++mm)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const float keep = b1 ? w4[4 * mm + 2 + k] : w4[4 * mm + k];
+              const float send = b1 ? w4[4 * mm + k] : w4[4 * mm + 2 + k];
+              a0[2 * mm + k] = keep;
+              a1[2 * mm + k] = __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+          float acc[X][4];              // slots: 0 = gate gam, 1 = gam^2, 2 = gam^1, 3 = gam^3
+#pragma unroll
+          for (int mm = 0; mm < X; ++mm) {
+            const float k0 = b0 ? a0[2 * mm + 1] : a0[2 * mm], s0 = b0 ? a0[2 * mm] : a0[2 * mm + 1];
+            const float k1 = b0 ? a1[2 * mm + 1] : a1[2 * mm], s1 = b0 ? a1[2 * mm] : a1[2 * mm + 1];
+            acc[mm][0] = k0;
+            acc[mm][1] = k1;
+            acc[mm][2] = __shfl_xor_sync(0xffffffffu, s0, 4);
+            acc[mm][3] = __shfl_xor_sync(0xffffffffu, s1, 4);
+          }
+          // gate g sits in slot (d>>1) | ((d&1)<<1), d = g ^ gam.  selp, not ?: chains: ptxas turned the 4-way
+          // compare chain into divergent branches (32 of them: 5200 cycles per tile)
+#pragma unroll
+          for (int mm = 0; mm < X; ++mm)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const bool x0 = b0 != ((g & 1) != 0), x1 = b1 != ((g & 2) != 0);
+              const float lo2 = fsel(x1, acc[mm][1], acc[mm][0]), hi2 = fsel(x1, acc[mm][3], acc[mm][2]);
+              pre[mm][g] += fsel(x0, hi2, lo2);
+            }
+          if (et == 0) TCU_TRACE(5, n);
+        }
+#pragma unroll
+        for (int mm = 0; mm < X; ++mm) {
+          const float gi = hsig_u(pre[mm][0]);
+          const float gf = hsig_u(pre[mm][1]);
+          const float gg = tanh_u(pre[mm][2]);
+          const float go = hsig_u(pre[mm][3]);
+          const float c = gf * c_state[tau][mm] + gi * gg;
+          c_state[tau][mm] = c;
+          const float h = go * tanh_u(c);
+          *reinterpret_cast<float*>(ystage + coff[mm]) = h;
+          if (p.save) {
+            *reinterpret_cast<float*>(cstage + coff[mm]) = c;
+            *reinterpret_cast<float*>(io + 0 * kYs + coff[mm]) = gi;
+            *reinterpret_cast<float*>(io + 1 * kYs + coff[mm]) = gf;
+            *reinterpret_cast<float*>(io + 2 * kYs + coff[mm]) = gg;
+            *reinterpret_cast<float*>(io + 3 * kYs + coff[mm]) = go;
+          }
+        }
+        if (et == 0) TCU_TRACE(10, n);
+        if (s + 1 < T) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");    // y tile staged
+          if (et < 2 * NB) {
+            float hv[16];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              const float4 f = *reinterpret_cast<const float4*>(ystage + sw64u((uint32_t)prow, (uint32_t)ch));
+              hv[4 * ch] = f.x; hv[4 * ch + 1] = f.y; hv[4 * ch + 2] = f.z; hv[4 * ch + 3] = f.w;
+            }
+            uint32_t w[8];
+#pragma unroll
+            for (int u = 0; u < 16; u += 2) {
+              const __nv_bfloat162 hh = __floats2bfloat162_rn(hv[u], hv[u + 1]);
+              uint32_t wv = *reinterpret_cast<const uint32_t*>(&hh);
+              if (ppart) {
+                const float f0 = __uint_as_float(wv << 16), f1 = __uint_as_float(wv & 0xffff0000u);
+                const __nv_bfloat162 ll = __floats2bfloat162_rn(hv[u] - f0, hv[u + 1] - f1);
+                wv = *reinterpret_cast<const uint32_t*>(&ll);
+              }
+              w[u >> 1] = wv;
+            }
+            const size_t rowR = (size_t)(dir * 2 + (s & 1)) * p.Bpad + (size_t)(2 * sb + tau) * NB + prow;
+            uint8_t* dst = p.hx + (((size_t)(j0 >> 6) * 2 + ppart) * R + rowR) * 128 + (size_t)(j0 & 63) * 2;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(dst + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+          }
+          if (et == 0) TCU_TRACE(6, n);
+          // One release per warp (8 increments per CTA and step): it is cumulative over the lanes' stores ordered
+          // before it by bar.warp.sync, the eight fences wait for their own warp's stores side by side, and no
+          // second CTA barrier sits in the chain (bar.sync + one MEMBAR.GPU + RED by a single thread: ~1900 cycles).
+          __syncwarp();
+          if (lane == 0) {
+            unsigned* ctr = p.counters + (dir * p.NTg + 2 * sb + tau) * 32;
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+          }
+          if (et == 0) TCU_TRACE(8, n);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive_u(&stage_ready[slot]);
+      }
+    }
+  } else if (warp == 10) {
+    // ---- IO warp: P loads two (step, tile) slots ahead, y / c / gates stores; box = 16 units x NB rows x 1 step
+    if (lane == 0) {
+      const int total = T * ntl;
+      for (int n = 0; n < min(2, total); ++n) {
+        const int s = n / ntl, tau = n - s * ntl;
+        mbar_expect_tx(&p_full[n & 1], kIo);
+        tma_load_4d_u(slots + (size_t)(n & 1) * kSlot, &tmG, &p_full[n & 1], j0, (2 * sb + tau) * NB, dir == 0 ? s : T - 1 - s, dir * 4);
+      }
+      int s = 0, tau = 0;
+      for (int n = 0; n < total; ++n) {
+        const int slot = n & 1;
+        uint8_t* io = slots + (size_t)slot * kSlot;
+        const int t = dir == 0 ? s : T - 1 - s;
+        const int b0 = (2 * sb + tau) * NB;
+        mbar_wait(&stage_ready[slot], (uint32_t)(n >> 1) & 1u);
+        tma_store_4d_u(&tmY, io + kIo, j0, b0, t, dir);
+        if (p.save) {
+          tma_store_4d_u(&tmC, io + kIo + kYs, j0, b0, t, dir);
+          tma_store_4d_u(&tmG, io, j0, b0, t, dir * 4);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        // slot free again: P of (step, tile) sequence number n + 2
+        int s2 = s, tau2 = tau;
+        for (int a = 0; a < 2; ++a) { if (++tau2 == ntl) { tau2 = 0; ++s2; } }
+        if (s2 < T) {
+          mbar_expect_tx(&p_full[slot], kIo);
+          tma_load_4d_u(io, &tmG, &p_full[slot], j0, (2 * sb + tau2) * NB, dir == 0 ? s2 : T - 1 - s2, dir * 4);
+        }
+        if (++tau == ntl) { tau = 0; ++s; }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+int split_bf16_t_launch(const float* x, int R, int K, int ldx, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_out,
+                        cudaStream_t s);
+
+struct TcuLayout {
+  int NB, NTg, NSB, Bpad, UGn, Kc, KS, Kp8, CP, NREQ;
+  size_t off_hx, off_ut_hi, off_ut_lo, off_trace, total, smem;
+};
+static TcuLayout tcu_layout(int B, int H) {
+  TcuLayout L;
+  int nb = 16;
+  while (nb < 128 && 2 * nb < B) nb *= 2;
+  if (const char* e = getenv("GR_TCU_NB")) {   // experiments: force the tile width
+    const int v = atoi(e);
+    if (v == 16 || v == 32 || v == 64 || v == 128) nb = v;
+  }
+  L.NB = nb;
+  L.NTg = (B + nb - 1) / nb;
+  L.NSB = (L.NTg + 1) / 2;
+  L.Bpad = L.NTg * nb;
+  L.UGn = (H + kUUnits - 1) / kUUnits;
+  L.Kc = (H + 63) / 64;
+  L.KS = (H + 15) / 16;
+  L.Kp8 = (H + 7) / 8 * 8;
+  L.CP = 128 / nb < L.Kc ? 128 / nb : L.Kc;
+  L.NREQ = (L.Kc + L.CP - 1) / L.CP;
+  L.smem = 1024 + (size_t)kURing * kUStage + (size_t)2 * nb * 384 + 256;
+  size_t o = (size_t)2 * L.NTg * 128;
+  o = (o + 1023) & ~(size_t)1023;
+  L.off_hx = o; o += (size_t)2 * L.Kc * 4 * L.Bpad * 128;
+  const size_t ut = (size_t)8 * H * L.Kp8 * 2;
+  L.off_ut_hi = o; o += (ut + 255) & ~(size_t)255;
+  L.off_ut_lo = o; o += (ut + 255) & ~(size_t)255;
+  L.off_trace = o; o += (size_t)160 * 256 * 16 * 8;
+  L.total = o + 256;
+  return L;
+}
+
+size_t lstm_tcu_workspace_bytes(int B, int H) { return tcu_layout(B, H).total; }
+size_t lstm_tcu_trace_offset(int B, int H) { return tcu_layout(B, H).off_trace; }
+
+bool lstm_tcu_supported(int B, int H) {
+  if (H % 4 != 0 || H < 32 || H > 512) return false;
+  TcuLayout L = tcu_layout(B, H);
+  return 2 * L.NSB * L.UGn <= num_sms() && 2 * L.NSB * L.UGn <= 160;
+}
+
+static int make_io_map_u(CUtensorMap* tm, const float* base, int B, int T, int H, int nvar, int nb, int nbox) {
+  const cuuint64_t dims[4] = {(cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)T, (cuuint64_t)nvar};
+  const cuuint64_t strides[3] = {(cuuint64_t)T * nvar * H * 4, (cuuint64_t)nvar * H * 4, (cuuint64_t)H * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)kUUnits, (cuuint32_t)nb, 1, (cuuint32_t)nbox};
+  return make_map_nd(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+int lstm_fwd_tcu_launch(float* gates, const float* U, int B, int T, int H, float* y, float* cell, void* workspace,
+                        cudaStream_t s) {
+  TcuLayout L = tcu_layout(B, H);
+  char* w = static_cast<char*>(workspace);
+  LstmTcuParams p;
+  p.save = cell != nullptr;
+  p.hx = reinterpret_cast<uint8_t*>(w + L.off_hx);
+  p.counters = reinterpret_cast<unsigned*>(w);
+  p.dbg = getenv("GR_TCU_DBG") ? atoi(getenv("GR_TCU_DBG")) : 0;
+  p.trace = getenv("GR_TC_TRACE") ? reinterpret_cast<long long*>(w + L.off_trace) : nullptr;
+  p.B = B; p.T = T; p.H = H; p.Bpad = L.Bpad; p.UGn = L.UGn; p.NTg = L.NTg; p.NSB = L.NSB; p.Kc = L.Kc; p.KS = L.KS;
+  p.Kp8 = L.Kp8; p.CP = L.CP; p.NREQ = L.NREQ;
+  GR_CUDA(cudaMemsetAsync(w, 0, L.off_ut_hi, s));   // counters + exchange buffer (its K padding stays zero)
+  __nv_bfloat16* ut_hi = reinterpret_cast<__nv_bfloat16*>(w + L.off_ut_hi);
+  __nv_bfloat16* ut_lo = reinterpret_cast<__nv_bfloat16*>(w + L.off_ut_lo);
+  p.ut_hi = ut_hi; p.ut_lo = ut_lo;
+  for (int d = 0; d < 2; ++d) {
+    int rc0 = split_bf16_t_launch(U + (size_t)d * H * 4 * H, H, 4 * H, 4 * H, ut_hi + (size_t)d * 4 * H * L.Kp8,
+                                  ut_lo + (size_t)d * 4 * H * L.Kp8, L.Kp8, s);
+    if (rc0 != GR_OK) return rc0;
+  }
+  CUtensorMap tH, tG, tY, tC;
+  int rc;
+  {
+    const cuuint64_t R = (cuuint64_t)4 * L.Bpad;
+    const cuuint64_t dims[3] = {64, R, (cuuint64_t)2 * L.Kc};
+    const cuuint64_t strides[2] = {128, R * 128};
+    const cuuint32_t box[3] = {64, (cuuint32_t)L.NB, (cuuint32_t)(2 * L.CP)};
+    if ((rc = make_map_nd(&tH, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p.hx, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) != GR_OK)
+      return rc;
+  }
+  if ((rc = make_io_map_u(&tG, gates, B, T, H, 8, L.NB, 4)) != GR_OK) return rc;
+  if ((rc = make_io_map_u(&tY, y, B, T, H, 2, L.NB, 1)) != GR_OK) return rc;
+  if ((rc = make_io_map_u(&tC, cell ? cell : y, B, T, H, 2, L.NB, 1)) != GR_OK) return rc;
+  void* args[] = {&tH, &tG, &tY, &tC, &p};
+  const dim3 grid(2 * L.NSB * L.UGn), block(kUThreads);
+  auto go = [&](auto kern) -> int {
+    GR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    GR_CUDA(cudaLaunchCooperativeKernel((void*)kern, grid, block, args, L.smem, s));
+    return GR_OK;
+  };
+  switch (L.NB) {
+    case 16: return go(lstm_fwd_tcu_kernel<16>);
+    case 32: return go(lstm_fwd_tcu_kernel<32>);
+    case 64: return go(lstm_fwd_tcu_kernel<64>);
+    default: return go(lstm_fwd_tcu_kernel<128>);
+  }
+}
+
+}  // namespace gr

@@ -46,11 +46,17 @@ def weight_table(model, prefix=""):
         t[prefix + "dense_1"] = [(prefix + "dense_1/kernel:0", d[0]), (prefix + "dense_1/bias:0", d[1])]
         return t
     if isinstance(model, FusionNet):
-        # multimodal.py builds: speech layers[2], layers[3], skeletal layers[2], layers[3], new BLSTM(100), Dense
-        for name, tower in (("speech/", model.speech), ("skeletal/", model.skeletal)):
-            sub = weight_table(tower, prefix=name)
-            sub.pop(name + "dense_1")          # the uni-modal heads are not part of the fusion graph
-            t.update(sub)
+        # Keras 2.1.4 `Container.layers` is sorted by DEPTH (distance from the output), ties in the order the graph
+        # walk from the outputs first met the layer.  In multimodal.py:109-118 both towers hang off the Merge at the
+        # same depths, so the saved fusion file (and topological `load_weights`) interleaves them:
+        #   speech_blstm_1 (depth 8), skeletal_blstm_1 (8), speech_blstm_2 (7), skeletal_blstm_2 (7),
+        #   the new Bidirectional (4), dense_1 (2)   -- layer names as renamed at multimodal.py:121-128;
+        # the uni-modal heads are not part of the fusion graph.
+        for lname, lstm, layer in (("speech_blstm_1", "blstm_1", model.speech.blstm_1),
+                                   ("skeletal_blstm_1", "blstm_1", model.skeletal.blstm_1),
+                                   ("speech_blstm_2", "blstm_2", model.speech.blstm_2),
+                                   ("skeletal_blstm_2", "blstm_2", model.skeletal.blstm_2)):
+            t[lname] = _blstm_entries(lname, lstm, layer)
         t["bidirectional_3"] = _blstm_entries("bidirectional_3", "blstm_2", model.blstm_3)
         d = model.dense.get_weights()
         t["dense_1"] = [("dense_1/kernel:0", d[0]), ("dense_1/bias:0", d[1])]
@@ -69,9 +75,11 @@ def _assign(model, arrays):
         model.blstm_2.set_weights(take(6))
         model.dense.set_weights(take(2))
     else:
-        for tower in (model.speech, model.skeletal):
-            tower.blstm_1.set_weights(take(6))
-            tower.blstm_2.set_weights(take(6))
+        # depth order of the fusion graph (see weight_table): s1, k1, s2, k2
+        model.speech.blstm_1.set_weights(take(6))
+        model.skeletal.blstm_1.set_weights(take(6))
+        model.speech.blstm_2.set_weights(take(6))
+        model.skeletal.blstm_2.set_weights(take(6))
         model.blstm_3.set_weights(take(6))
         model.dense.set_weights(take(2))
     rest = list(it)

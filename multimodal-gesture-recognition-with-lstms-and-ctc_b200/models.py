@@ -144,7 +144,7 @@ class FusionNet(nn.Module):
                 merged = torch.empty(xa.shape[:2] + (fa + fs,), dtype=torch.float32, device=xa.device) if fused else None
                 ra = self.speech.tower(xa, reg.get("sp"), merged, 0)
                 rs = self.skeletal.tower(xs, reg.get("sk"), merged, fa)
-                return {"merged": merged if fused else ops.concat2(ra, rs), "events": []}
+                return {"merged": merged if fused else ops.concat2(ra, rs), "events": [], "inputs": (xa, xs)}
             merged = torch.empty(xa.shape[:2] + (fa + fs,), dtype=torch.float32, device=xa.device)
             cur = torch.cuda.current_stream()
             if self._streams is None:
@@ -270,11 +270,12 @@ class FusionTrainer:
         loss = trainer.step(batch_n, next_inputs=(xa_next, xs_next))     # batch = (xa, xs, labels, il, ll)
     """
 
-    def __init__(self, model, opt, seed=0, global_batch=None, grad_hook=None, hook_after_towers=False):
+    def __init__(self, model, opt, seed=0, global_batch=None, grad_hook=None, hook_after_towers=True):
         self.model, self.opt, self.seed, self.global_batch = model, opt, seed, global_batch
         self.grad_hook = grad_hook        # e.g. pack + all-reduce of the flat gradient bucket (data parallel)
-        # True: the calling stream waits for the prefetched towers before the hook runs, so that a collective in
-        # the hook never shares the GPU with the (cooperatively launched) recurrence kernels -- DESIGN 5
+        # True (default): the calling stream waits for the prefetched towers before the hook runs, so that a
+        # collective in the hook never shares the GPU with the (cooperatively launched, spinning) recurrence
+        # kernels -- DESIGN 5.  The next fusion step needs those towers anyway, so the wait is off the critical path.
         self.hook_after_towers = hook_after_towers
         self.step_no = 0                  # next step to be trained
         self._pending = None              # (step index, reg, towers handle)
@@ -292,7 +293,11 @@ class FusionTrainer:
         self._pending = None
         if pend is None or pend[0] != self.step_no or pend[2].get("inputs", (None, None))[0] is not xa \
                 or pend[2]["inputs"][1] is not xs:
-            pend = self._launch(xa, xs, self.step_no)          # cold start, or the prefetch was for other tensors
+            # cold start, or the prefetch was for other tensors.  A stale prefetch is JOINED before it is dropped:
+            # its `merged` / regulariser buffers were allocated on this stream while the side streams still work on
+            # them; releasing them un-joined would hand the blocks back to this stream's allocator pool mid-flight.
+            self._drain(pend)
+            pend = self._launch(xa, xs, self.step_no)
         _, reg, towers = pend
         if next_inputs is not None:
             self._pending = self._launch(next_inputs[0], next_inputs[1], self.step_no + 1, next_ready)
@@ -305,6 +310,21 @@ class FusionTrainer:
         self.opt.step(grads)
         self.step_no += 1
         return loss
+
+    def _drain(self, pend):
+        if pend is not None:
+            self.model.join_towers(pend[2])
+
+    def close(self):
+        """Join a prefetch that will never be consumed (last `next_inputs` of an epoch) before its buffers go."""
+        pend, self._pending = self._pending, None
+        self._drain(pend)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def fusion_optimizer(model):

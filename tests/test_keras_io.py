@@ -25,8 +25,9 @@ def test_weight_names_and_order_follow_keras():
     b = t["bidirectional_1"][2][1]
     assert np.all(b[8:16] == 1) and np.all(b[:8] == 0) and np.all(b[16:] == 0)
     tf = keras_io.weight_table(fu)
-    assert list(tf) == ["speech/bidirectional_1", "speech/bidirectional_2", "skeletal/bidirectional_1",
-                        "skeletal/bidirectional_2", "bidirectional_3", "dense_1"]
+    # Keras depth order of the fusion graph: the two towers interleave (multimodal.py:109-128)
+    assert list(tf) == ["speech_blstm_1", "skeletal_blstm_1", "speech_blstm_2", "skeletal_blstm_2",
+                        "bidirectional_3", "dense_1"]
     assert tf["bidirectional_3"][0][1].shape == (2 * 8 + 2 * 6, 16)
 
 
@@ -65,3 +66,36 @@ def test_load_rejects_wrong_topology(tmp_path):
         keras_io.load_weights(sk, p)         # same number of arrays, different shapes
     with pytest.raises(ValueError):
         keras_io.load_weights(fu, p)         # different number of arrays
+
+
+def test_fusion_file_laid_out_as_keras_writes_it(tmp_path):
+    """A fusion checkpoint as Keras 2.1.4 saves it: layers in DEPTH order -- speech_blstm_1, skeletal_blstm_1,
+    speech_blstm_2, skeletal_blstm_2, bidirectional_3, dense_1 -- each Bidirectional as forward (kernel, recurrent,
+    bias) then backward.  Built by hand here (not through save_weights) and loaded positionally."""
+    from mgr_b200 import keras_io
+    sp, sk, fu = _nets()
+    rng = np.random.default_rng(5)
+    Hs, Hk, Hf = 8, 6, 4
+
+    def blstm(F, H):
+        return [rng.standard_normal(s).astype(np.float32) for s in ((F, 4 * H), (H, 4 * H), (4 * H,)) * 2]
+    layers = {"speech_blstm_1": blstm(39, Hs), "skeletal_blstm_1": blstm(20, Hk), "speech_blstm_2": blstm(2 * Hs, Hs),
+              "skeletal_blstm_2": blstm(2 * Hk, Hk), "bidirectional_3": blstm(2 * Hs + 2 * Hk, Hf),
+              "dense_1": [rng.standard_normal((2 * Hf, 22)).astype(np.float32), rng.standard_normal(22).astype(np.float32)]}
+    order = ["speech_blstm_1", "skeletal_blstm_1", "speech_blstm_2", "skeletal_blstm_2", "bidirectional_3", "dense_1"]
+    flat = [(n, a) for n in order for a in layers[n]]
+    path = str(tmp_path / "fusion_as_keras.npz")
+    np.savez(path, **{"%03d|%s/w%d" % (i, n, i): a for i, (n, a) in enumerate(flat)})
+    keras_io.load_weights(fu, path)
+    for got, want in ((fu.speech.blstm_1, "speech_blstm_1"), (fu.skeletal.blstm_1, "skeletal_blstm_1"),
+                      (fu.speech.blstm_2, "speech_blstm_2"), (fu.skeletal.blstm_2, "skeletal_blstm_2"),
+                      (fu.blstm_3, "bidirectional_3"), (fu.dense, "dense_1")):
+        for a, b in zip(got.get_weights(), layers[want]):
+            assert np.array_equal(a, b)
+    # the tower-major order (speech 1, 2, skeletal 1, 2) is NOT what Keras writes: first mismatch (16,32) vs (20,24)
+    bad = [(n, a) for n in ["speech_blstm_1", "speech_blstm_2", "skeletal_blstm_1", "skeletal_blstm_2", "bidirectional_3",
+                            "dense_1"] for a in layers[n]]
+    path2 = str(tmp_path / "tower_major.npz")
+    np.savez(path2, **{"%03d|%s/w%d" % (i, n, i): a for i, (n, a) in enumerate(bad)})
+    with pytest.raises(ValueError):
+        keras_io.load_weights(fu, path2)

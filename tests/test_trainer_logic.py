@@ -74,8 +74,21 @@ def test_prefetch_for_other_tensors_is_discarded():
     t.step(a + (0, 0, 0), next_inputs=b)
     m.log.clear()
     t.step(other + (0, 0, 0))                         # the caller changed its mind: same step index, other tensors
-    assert [e[:2] for e in m.log] == [("reg", 1), ("towers", 1), ("fusion", 1)]
-    assert m.log[1][2] == id(other[0])
+    # the stale prefetch is JOINED before it is dropped (its buffers are still in use on the side streams)
+    assert m.log[0] == ("join", id(b[0]))
+    assert [e[:2] for e in m.log[1:]] == [("reg", 1), ("towers", 1), ("fusion", 1)]
+    assert m.log[2][2] == id(other[0])
+
+
+def test_unconsumed_prefetch_is_joined_on_close():
+    t, m, _ = _trainer()
+    a, b = (_T(), _T()), (_T(), _T())
+    t.step(a + (0, 0, 0), next_inputs=b)              # last next_inputs of an epoch, never trained on
+    m.log.clear()
+    t.close()
+    assert m.log == [("join", id(b[0]))]
+    t.close()                                         # idempotent
+    assert len(m.log) == 1
 
 
 def test_grad_hook_sits_between_backward_and_optimiser():
