@@ -302,7 +302,9 @@ static bool use_small_path(int H) {
 }
 static bool use_tcu_path(int B, int H) {
   const char* e = getenv("GR_LSTM_IMPL");
-  if (!e || strcmp(e, "tcu") != 0) return false;   // opt-in until it has passed the GPU parity tests
+  if (e) return strcmp(e, "tcu") == 0 && lstm_tcu_supported(B, H);
+  const char* d = getenv("GR_LSTM_TCU");           // default forward kernel for the wide layers; GR_LSTM_TCU=0: lstm_tc.cu
+  if (d && d[0] == '0') return false;
   return lstm_tcu_supported(B, H);
 }
 static bool use_tc_path(int B, int H) {

@@ -47,7 +47,7 @@ struct LstmTcuParams {
   const __nv_bfloat16* ut_lo;
   long long* trace;
   int B, T, H, Bpad, UGn, NTg, NSB, Kc, KS, Kp8, CP, NREQ, save;
-  int dbg;                     // GR_TCU_DBG experiments: 1 = MMAs of the next tile are NOT held back behind the epilogue's tcgen05.ld
+  int dbg;                     // GR_TCU_DBG experiments: 1 = MMAs of the next tile are NOT held back behind the epilogue's tcgen05.ld, 2 = no MMAs, 4 = no h loads
 };
 
 #define TCU_TRACE(slot, n) do { if (p.trace && (n) < 256) p.trace[((size_t)blockIdx.x * 256 + (n)) * 16 + (slot)] = clock64(); } while (0)
@@ -194,7 +194,7 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
       for (int tau = 0; tau < ntl; ++tau) {
         const int gt = 2 * sb + tau;
         const unsigned* ctr = p.counters + (dir * p.NTg + gt) * 32;
-        const unsigned target = (unsigned)s * p.UGn * 8u;   // 8 epilogue warps per CTA release once per step
+        const unsigned target = (unsigned)s * p.UGn;
         unsigned v;
         do {
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
@@ -203,10 +203,14 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
         if (lane == 0) TCU_TRACE(0, s * ntl + tau);
         const int row = (dir * 2 + ((s + 1) & 1)) * p.Bpad + gt * NB;
         for (int r = 0; r < p.NREQ; ++r) {
-          mbar_wait(&empty[st], ph ^ 1);
+          if ((st & 1) == 0) mbar_wait(&empty[st >> 1], ph ^ 1);   // stages are released in pairs (see the MMA warp)
           if (elect_one_u()) {
-            mbar_expect_tx(&full[st], stage_bytes);
-            tma_load_3d_u(ring + (size_t)st * kUStage, &tmH, &full[st], 0, row, 2 * p.CP * r);
+            if (p.dbg & 4) {
+              mbar_arrive_u(&full[st]);      // timing experiment: no h loads (results invalid)
+            } else {
+              mbar_expect_tx(&full[st], stage_bytes);
+              tma_load_3d_u(ring + (size_t)st * kUStage, &tmH, &full[st], 0, row, 2 * p.CP * r);
+            }
           }
           __syncwarp();
           if (++st == kURing) { st = 0; ph ^= 1; }
@@ -215,16 +219,19 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ---- MMA issue: D[tile] (128 x NB, fp32) = sum_k A[:, k] (TMEM) x (h_hi + h_lo)[tile rows, k]^T
+    // ---- MMA issue: D[tile] (128 x NB, fp32) = sum_k A[:, k] (TMEM) x (h_hi + h_lo)[tile rows, k]^T.
+    // A tcgen05.commit blocks the issuing thread for ~375 cycles (scripts/micro/umma_rate.cu): with one commit per
+    // 8-MMA stage the pipe ran at ~95 cycles per N=128 MMA instead of 69, so ring stages are released in PAIRS (one
+    // commit per two stages).  (Two issuing warps on alternate stages of the same accumulator were tried: faster,
+    // but MMAs of different threads into one accumulator are not interlocked -- 6 of 22 parity cases failed.)
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     int st = 0;
     uint32_t ph = 0;
     for (int s = 1; s < T; ++s) {
       for (int tau = 0; tau < ntl; ++tau) {
         const uint32_t dcol = tmem_base + kDBase + (uint32_t)(tau * NB);
-        // A tcgen05.ld issued while MMAs are queued is served behind them (measured: the epilogue's two loads took
-        // ~5400 cycles = the other tile's whole MMA phase), so this tile's MMAs are not issued before the epilogue
-        // has the previous tile's accumulator in registers; the rest of that epilogue overlaps with them.
+        // A tcgen05.ld issued while MMAs are queued is served behind them, so this tile's MMAs are not issued before
+        // the epilogue has the previous tile's accumulator in registers; the rest of that epilogue overlaps with them.
         const int m = (s - 1) * ntl + tau;
         if (m > 0 && !(p.dbg & 1)) mbar_wait(ld_done, (uint32_t)((m - 1) & 1));
         for (int r = 0; r < p.NREQ; ++r) {
@@ -239,13 +246,13 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
               const uint64_t dBh = make_sw128_desc(sa + (uint32_t)(cc * 2) * (NB * 128u));
               const uint64_t dBl = make_sw128_desc(sa + (uint32_t)(cc * 2 + 1) * (NB * 128u));
               const int nk = min(4, p.KS - 4 * c);
-              for (int k = 0; k < nk; ++k) {
+              for (int k = 0; k < nk && !(p.dbg & 2); ++k) {   // dbg 2: timing experiment without MMAs (results invalid)
                 const uint32_t a = tmem_base + (uint32_t)((4 * c + k) * 8);
                 umma_ts_bf16(dcol, a, dBh + (uint64_t)(k * 2), idesc, (c > 0 || k > 0) ? 1u : 0u);
                 umma_ts_bf16(dcol, a, dBl + (uint64_t)(k * 2), idesc, 1u);
               }
             }
-            umma_commit(&empty[st]);
+            if (st & 1) umma_commit(&empty[st >> 1]);   // stages st-1 and st are free once these MMAs are done
           }
           __syncwarp();
           if (++st == kURing) { st = 0; ph ^= 1; }
@@ -403,11 +410,12 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
             *reinterpret_cast<uint4*>(dst + 16) = make_uint4(w[4], w[5], w[6], w[7]);
           }
           if (et == 0) TCU_TRACE(6, n);
-          // One release per warp (8 increments per CTA and step): it is cumulative over the lanes' stores ordered
-          // before it by bar.warp.sync, the eight fences wait for their own warp's stores side by side, and no
-          // second CTA barrier sits in the chain (bar.sync + one MEMBAR.GPU + RED by a single thread: ~1900 cycles).
-          __syncwarp();
-          if (lane == 0) {
+          // the release below is cumulative over everything ordered before it by bar.sync (lstm_tc.cu).  (One release
+          // per warp after bar.warp.sync instead -- 8 MEMBAR.GPU side by side, no second CTA barrier -- was measured
+          // SLOWER: red done at +4855 instead of +4137 cycles after tmem_full.)
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (et == 0) {
+            TCU_TRACE(7, n);
             unsigned* ctr = p.counters + (dir * p.NTg + 2 * sb + tau) * 32;
             asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
           }

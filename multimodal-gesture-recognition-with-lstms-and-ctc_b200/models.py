@@ -153,7 +153,10 @@ class FusionNet(nn.Module):
             sa, sb, sc, sd = self._streams
             B = xa.shape[0]
             work = []
-            split = os.environ.get("GR_TOWER_SPLIT", "2")
+            # lstm_tcu.cu (default) runs a whole 256-sequence layer on 64 / 38 CTAs, so both towers fit side by side
+            # unsplit (43.0 ms/step against 48.9 with halves); the half-batch schedule below is what the round-1
+            # kernel (GR_LSTM_TCU=0: 128 CTAs per speech layer) needs.
+            split = os.environ.get("GR_TOWER_SPLIT", "2" if os.environ.get("GR_LSTM_TCU") == "0" else "0")
             if B >= 2 * SPLIT_MIN_HALF and split in ("1", "2"):
                 # The speech recurrence of a 256-sequence batch holds 128 SMs (2 directions x 2 batch tiles x 32
                 # unit slices, one CTA per SM), so the skeletal recurrence (76 CTAs) cannot run beside it.  Two

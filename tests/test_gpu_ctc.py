@@ -90,14 +90,11 @@ def test_chunk_boundaries_and_both_kernels(cuda, monkeypatch, impl, Tn):
     assert np.abs(grad2 - ref_g2).max() <= GRAD_TOL * np.abs(ref_g2).max()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("GR_RUN_UNVERIFIED") != "1",
-                    reason="added after round 1's GPU budget was spent: the 16- and 8-frame chunk instantiations (only "
-                           "picked for very large batches) have not run on a GPU yet; a fault in an unverified kernel "
-                           "would poison the CUDA context for the rest of the suite, so it runs on request only")
 @pytest.mark.parametrize("tc", ["16", "8"])
 def test_small_chunk_instantiations(cuda, monkeypatch, tc):
     """The chunk size is chosen from the batch size (shared memory for a single wave); small test batches always
-    get 32 frames, so force the other two template instantiations (GR_CTC_TC)."""
+    get 32 frames, so force the other two template instantiations (GR_CTC_TC).  (First run on a GPU in round 2,
+    also under compute-sanitizer memcheck: profiles/r02_sanitizer_ctc_small_chunks.txt.)"""
     import mgr_b200 as mgr
     from oracle import ctc_ref
     monkeypatch.setenv("GR_CTC_TC", tc)
@@ -172,10 +169,38 @@ def test_full_size_properties(cuda):
     assert gsum < 1e-4
     assert torch.all(y.grad[:, :2] == 0)
     assert torch.isfinite(loss).all()
-    idx = [0, 511, 1023]
+    idx = sorted(set([0, 511, 1023]) | set(np.random.default_rng(7).choice(B, 64, replace=False).tolist()))
     ref_loss, ref_g = ctc_ref.softmax_ctc_grad_logits(a[idx].cpu().numpy(), labels[idx], il[idx], ll[idx],
-                                                      upstream=np.ones(3))
+                                                      upstream=np.ones(len(idx)))
     got = loss[idx].detach().cpu().numpy()
     assert np.abs(got - ref_loss).max() <= LOSS_RTOL * np.abs(ref_loss).max()
     gg = y.grad[idx].cpu().numpy()
     assert np.abs(gg - ref_g).max() <= GRAD_TOL * np.abs(ref_g).max()
+
+
+@pytest.mark.parametrize("B,T,C,Lmax,ragged", [(1024, 402, 44, 40, False), (512, 602, 44, 150, True), (700, 302, 22, 150, True)])
+def test_large_batch_chunk_selection(cuda, B, T, C, Lmax, ragged):
+    """Shapes at which `launch_ctc` picks the 16- / 8-frame chunk instantiations BY ITSELF (one wave of CTAs no longer
+    fits with 32-frame chunks): BASELINE config 4's "also C=44" at B=1024, and the speech net's Lmax=150
+    (audio_network/data_generator.py absolute_max_sequence_len) at large batch.  64 random sequences vs the oracle."""
+    import mgr_b200 as mgr
+    from oracle import ctc_ref
+    g = torch.Generator(device="cpu").manual_seed(B + C)
+    a = (torch.randn(B, T, C, generator=g) * 2).to(cuda)
+    rng = np.random.default_rng(B * 7 + Lmax)
+    il = rng.integers((T - 2) // 2, T - 1, size=(B, 1)) if ragged else np.full((B, 1), T - 2)
+    labels, ll = random_labels(rng, B, Lmax, C, T_avail=il[:, 0])
+    y = a.clone().requires_grad_(True)
+    loss = mgr.softmax_ctc(y, torch.tensor(labels), torch.tensor(il), torch.tensor(ll))
+    loss.sum().backward()
+    fin = torch.isfinite(loss).cpu().numpy().ravel()
+    assert y.grad.sum(dim=2).abs().max().item() < 1e-4
+    idx = np.random.default_rng(11).choice(B, 64, replace=False)
+    ref_loss, ref_g = ctc_ref.softmax_ctc_grad_logits(a[idx].cpu().numpy(), labels[idx], il[idx], ll[idx],
+                                                      upstream=np.ones(len(idx)))
+    got = loss[idx].detach().cpu().numpy()
+    f = np.isfinite(ref_loss).ravel()
+    assert np.array_equal(f, fin[idx])
+    assert np.abs(got.ravel()[f] - ref_loss.ravel()[f]).max() <= LOSS_RTOL * np.abs(ref_loss.ravel()[f]).max()
+    gg = y.grad[idx].cpu().numpy()
+    assert np.abs(gg[f] - ref_g[f]).max() <= GRAD_TOL * np.abs(ref_g[f]).max()

@@ -117,10 +117,12 @@ def test_long_sequence_stability(cuda):
 
 
 @pytest.mark.parametrize("impl,B,T,F,H", [("generic", 5, 9, 16, 36), ("tc", 5, 9, 16, 36), ("tc", 130, 6, 24, 100),
-                                          ("small", 9, 11, 16, 100), ("generic", 9, 7, 16, 100)])
+                                          ("small", 9, 11, 16, 100), ("generic", 9, 7, 16, 100),
+                                          ("tcu", 5, 9, 16, 36), ("tcu", 130, 6, 24, 100), ("tcu", 40, 7, 20, 300),
+                                          ("tcu", 70, 5, 12, 500)])
 def test_every_recurrence_implementation(cuda, monkeypatch, impl, B, T, F, H):
-    """The three recurrence kernels (generic fp32 / tcgen05 / register-resident) agree with the
-    oracle on the same inputs (GR_LSTM_IMPL forces one)."""
+    """The recurrence kernels (generic fp32 / tcgen05 with U in shared memory / tcgen05 with U in tensor memory /
+    register-resident) agree with the oracle on the same inputs (GR_LSTM_IMPL forces one)."""
     import mgr_b200 as mgr
     monkeypatch.setenv("GR_LSTM_IMPL", impl)
     for attempt in range(20):
@@ -165,3 +167,37 @@ def test_full_size_recurrence_properties(cuda, monkeypatch):
     monkeypatch.setenv("GR_LSTM_IMPL", "generic")
     y_gen, _ = ops.lstm_recurrence_fwd(sub.clone(), U, rows.numel(), T, H, keep_cell=False)
     assert (y_sub - y_gen).abs().max().item() <= 2e-4
+
+
+@pytest.mark.parametrize("impl", ["tcu", "tc"])
+def test_bench_size_recurrence_against_fp64(cuda, monkeypatch, impl):
+    """Bench-size layer (B=256, H=500: two 128-row tiles per CTA in lstm_tcu.cu) against an fp64 recurrence on the same
+    pre-activations, inference and training mode (saved gates and cell state), T=40."""
+    from mgr_b200 import ops
+    monkeypatch.setenv("GR_LSTM_IMPL", impl)
+    B, T, H = 256, 40, 500
+    rng = np.random.default_rng(17)
+    P = (rng.standard_normal((B, T, 8 * H)) * 0.7).astype(np.float32)
+    U = (rng.standard_normal((2, H, 4 * H)) / np.sqrt(H)).astype(np.float32)
+    hs = lambda v: np.clip(0.2 * v + 0.5, 0, 1)
+    y_ref = np.zeros((B, T, 2 * H)); c_ref = np.zeros((B, T, 2 * H)); g_ref = np.zeros((B, T, 8 * H))
+    P64, U64 = P.astype(np.float64), U.astype(np.float64)
+    for d in range(2):
+        h = np.zeros((B, H)); c = np.zeros((B, H))
+        for s in range(T):
+            t = s if d == 0 else T - 1 - s
+            z = P64[:, t, d * 4 * H:(d + 1) * 4 * H] + h @ U64[d]
+            i, f, g_, o = hs(z[:, :H]), hs(z[:, H:2 * H]), np.tanh(z[:, 2 * H:3 * H]), hs(z[:, 3 * H:])
+            c = f * c + i * g_
+            h = o * np.tanh(c)
+            y_ref[:, t, d * H:(d + 1) * H] = h
+            c_ref[:, t, d * H:(d + 1) * H] = c
+            g_ref[:, t, d * 4 * H:(d + 1) * 4 * H] = np.concatenate([i, f, g_, o], 1)
+    U_d = torch.tensor(U, device=cuda)
+    for keep in (False, True):
+        g = torch.tensor(P.reshape(B * T, 8 * H), device=cuda)
+        y, cell = ops.lstm_recurrence_fwd(g, U_d, B, T, H, keep_cell=keep)
+        assert np.abs(y.cpu().numpy() - y_ref).max() <= 2e-4
+        if keep:
+            assert np.abs(cell.cpu().numpy() - c_ref).max() <= 5e-4
+            assert np.abs(g.cpu().numpy().reshape(B, T, 8 * H) - g_ref).max() <= 2e-4
