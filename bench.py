@@ -344,14 +344,14 @@ def run_gpu(args):
     # FusionTrainer = the reference's training step (forward, CTC objective, all-reduce, Adam/clip/maxnorm) with the
     # frozen towers of the NEXT batch enqueued beside the fusion layer of this one (GR_PIPELINE=0: strictly serial)
     trainer = mgr.FusionTrainer(model, opt, seed=1234 + rank, global_batch=GLOBAL_BATCH, grad_hook=reduce_grads)
-    # Multi-GPU default: OFF.  With the pipeline the towers of batch n+1 (persistent recurrence kernels whose CTAs
-    # spin on each other) share the GPU with the NCCL all-reduce of step n; N=2 ran clean with it twice (10.7k seq/s)
-    # but one N=2 run and the only N=4 run of round 1 did not finish, so until that is understood the data-parallel
-    # runs use the strictly serial step that rounds of N=2/N=4 runs have validated.  GR_PIPELINE=1 forces it on.
-    # GR_PIPELINE=2: pipeline on, but the all-reduce waits for the prefetched towers (candidate fix, not yet run).
-    pmode = os.environ.get("GR_PIPELINE", "1" if world == 1 else "0")
-    pipeline = pmode in ("1", "2")
-    trainer.hook_after_towers = pmode == "2"
+    # GR_PIPELINE: 1 (default at every N) = towers one batch ahead, the all-reduce of step n ordered BEHIND the
+    # prefetched towers of batch n+1 (FusionTrainer.hook_after_towers: a collective never shares the GPU with the
+    # spinning cooperative recurrence kernels -- the combination that did not finish in two round-1 runs; the next
+    # fusion step needs those towers anyway, so nothing on the critical path waits longer);  0 = strictly serial;
+    # 3 = pipeline with the all-reduce free to overlap the towers (round-1 behaviour, for investigation only).
+    pmode = os.environ.get("GR_PIPELINE", "1")
+    pipeline = pmode in ("1", "2", "3")
+    trainer.hook_after_towers = pmode != "3"
 
     def train_step(xa, xs, lab, il, ll, nxt=None, nxt_ready=None):
         return trainer.step((xa, xs, lab, il, ll), next_inputs=nxt if pipeline else None, next_ready=nxt_ready)
