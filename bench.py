@@ -330,6 +330,8 @@ def run_gpu(args):
     B = hi - lo
     T = args.seq_len
 
+    if os.environ.get("GR_MAIN_PRIO"):   # experiment: the fusion layer's stream above the towers' streams
+        torch.cuda.set_stream(torch.cuda.Stream(priority=int(os.environ["GR_MAIN_PRIO"])))
     model = mgr.FusionNet().to(dev)
     opt = mgr.fusion_optimizer(model)
     bucket = parallel.FlatGradBucket(model.trainable_parameters())

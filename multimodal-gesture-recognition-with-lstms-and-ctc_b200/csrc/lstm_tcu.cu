@@ -109,6 +109,11 @@ __global__ void __launch_bounds__(kUThreads, 1)
 lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmG,
                     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmC, LstmTcuParams p) {
   constexpr int X = NB / 16;                    // 8-column groups per epilogue warp (each warp: NB/2 columns)
+  // Narrow tiles: ONE MMA per k-step with N = 2 NB over the stacked [h_hi rows ; h_lo rows] slabs (they are adjacent
+  // in the stage), D columns [0, NB) = A h_hi^T and [NB, 2NB) = A h_lo^T, added in the epilogue.  At N = 16 / 32 the
+  // issue rate (~23 cycles per MMA), not the tensor pipe, bounds the MMA phase: half the instructions, half the time.
+  constexpr bool STK = NB <= 32;
+  constexpr int DW = STK ? 2 * NB : NB;         // accumulator columns per tile
   constexpr uint32_t kIo = NB * 256;            // P / gates tile: [4 gates][NB rows][16 units] fp32
   constexpr uint32_t kYs = NB * 64;             // y (and c) staging: [NB rows][16 units] fp32
   constexpr uint32_t kSlot = kIo + 2 * kYs;
@@ -132,6 +137,10 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
   const int H = p.H, T = p.T;
   const int ntl = min(2, p.NTg - 2 * sb);               // tiles of this CTA
   const uint32_t stage_bytes = (uint32_t)p.CP * 2u * NB * 128u;
+  // When one step's requests of all tiles fit the ring, a stage is only re-used by the SAME tile's next step, whose h
+  // exists only after this CTA's epilogue saw the tile's MMAs complete (tmem_full): the stage-release commits (each
+  // blocks the MMA warp for ~375 cycles) are implied by the data dependence and are skipped.
+  const bool need_empty = ntl * p.NREQ > kURing;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmH)) : "memory");
@@ -203,7 +212,7 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
         if (lane == 0) TCU_TRACE(0, s * ntl + tau);
         const int row = (dir * 2 + ((s + 1) & 1)) * p.Bpad + gt * NB;
         for (int r = 0; r < p.NREQ; ++r) {
-          if ((st & 1) == 0) mbar_wait(&empty[st >> 1], ph ^ 1);   // stages are released in pairs (see the MMA warp)
+          if (need_empty && (st & 1) == 0) mbar_wait(&empty[st >> 1], ph ^ 1);   // stages are released in pairs (see the MMA warp)
           if (elect_one_u()) {
             if (p.dbg & 4) {
               mbar_arrive_u(&full[st]);      // timing experiment: no h loads (results invalid)
@@ -224,12 +233,12 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
     // 8-MMA stage the pipe ran at ~95 cycles per N=128 MMA instead of 69, so ring stages are released in PAIRS (one
     // commit per two stages).  (Two issuing warps on alternate stages of the same accumulator were tried: faster,
     // but MMAs of different threads into one accumulator are not interlocked -- 6 of 22 parity cases failed.)
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(DW >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     int st = 0;
     uint32_t ph = 0;
     for (int s = 1; s < T; ++s) {
       for (int tau = 0; tau < ntl; ++tau) {
-        const uint32_t dcol = tmem_base + kDBase + (uint32_t)(tau * NB);
+        const uint32_t dcol = tmem_base + kDBase + (uint32_t)(tau * DW);
         // A tcgen05.ld issued while MMAs are queued is served behind them, so this tile's MMAs are not issued before
         // the epilogue has the previous tile's accumulator in registers; the rest of that epilogue overlaps with them.
         const int m = (s - 1) * ntl + tau;
@@ -240,23 +249,34 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
           if (lane == 0 && r == 0) TCU_TRACE(2, s * ntl + tau);
           const uint32_t sa = smem_u32(ring + (size_t)st * kUStage);
           if (elect_one_u()) {
-            for (int cc = 0; cc < p.CP; ++cc) {
-              const int c = r * p.CP + cc;
-              if (c >= p.Kc) break;
-              const uint64_t dBh = make_sw128_desc(sa + (uint32_t)(cc * 2) * (NB * 128u));
-              const uint64_t dBl = make_sw128_desc(sa + (uint32_t)(cc * 2 + 1) * (NB * 128u));
-              const int nk = min(4, p.KS - 4 * c);
-              for (int k = 0; k < nk && !(p.dbg & 2); ++k) {   // dbg 2: timing experiment without MMAs (results invalid)
-                const uint32_t a = tmem_base + (uint32_t)((4 * c + k) * 8);
-                umma_ts_bf16(dcol, a, dBh + (uint64_t)(k * 2), idesc, (c > 0 || k > 0) ? 1u : 0u);
-                umma_ts_bf16(dcol, a, dBl + (uint64_t)(k * 2), idesc, 1u);
+            // running descriptor / address increments only: a lone warp executes dependent scalar code at ~4-5 cycles
+            // per instruction, and the per-chunk index arithmetic of the first version cost ~140 cycles per chunk
+            // (more than the four MMAs of a narrow tile)
+            constexpr uint64_t kSlab = (uint64_t)((NB * 128u) >> 4);     // descriptor units per [NB rows x 64 k] slab
+            int c = r * p.CP;
+            const int cend = (p.dbg & 2) ? c : min(p.Kc, c + p.CP);      // dbg 2: timing experiment without MMAs
+            uint64_t dB = make_sw128_desc(sa);                           // hi slab of the stage's first chunk
+            uint32_t a = tmem_base + (uint32_t)(c * 32);                 // 4 k-steps x 8 columns per chunk
+            uint32_t acc = c > 0 ? 1u : 0u;
+            for (; c < cend; ++c) {
+              const int nk = p.KS - 4 * c;                               // < 4 only in the last chunk
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k < nk) {
+                  umma_ts_bf16(dcol, a + (uint32_t)(8 * k), dB + (uint64_t)(2 * k), idesc, k > 0 ? 1u : acc);
+                  if (!STK) umma_ts_bf16(dcol, a + (uint32_t)(8 * k), dB + kSlab + (uint64_t)(2 * k), idesc, 1u);
+                }
               }
+              acc = 1u;
+              a += 32u;
+              dB += 2 * kSlab;
             }
-            if (st & 1) umma_commit(&empty[st >> 1]);   // stages st-1 and st are free once these MMAs are done
+            if (need_empty && (st & 1)) umma_commit(&empty[st >> 1]);   // stages st-1 and st are free once these MMAs are done
           }
           __syncwarp();
           if (++st == kURing) { st = 0; ph ^= 1; }
         }
+        if (lane == 0) TCU_TRACE(15, s * ntl + tau);
         if (elect_one_u()) umma_commit(&tmem_full[tau]);
         __syncwarp();
         if (lane == 0) TCU_TRACE(3, s * ntl + tau);
@@ -310,9 +330,17 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
           if (et == 0) TCU_TRACE(4, n);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           uint32_t v[8 * X];          // this thread's row, columns hw*NB/2 + [0, 8X)
-          const uint32_t taddr = tmem_base + kDBase + (uint32_t)(tau * NB + hw * (NB / 2)) + ((uint32_t)(q * 32) << 16);
+          const uint32_t taddr = tmem_base + kDBase + (uint32_t)(tau * DW + hw * (NB / 2)) + ((uint32_t)(q * 32) << 16);
 #pragma unroll
           for (int j = 0; j < X; ++j) tmem_ld_32x8(taddr + (uint32_t)(8 * j), v + 8 * j);
+          if constexpr (STK) {
+            uint32_t v2[8 * X];         // the h_lo half of the stacked accumulator
+#pragma unroll
+            for (int j = 0; j < X; ++j) tmem_ld_32x8(taddr + (uint32_t)(NB + 8 * j), v2 + 8 * j);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 8 * X; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+          }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (et == 0) TCU_TRACE(12, n);
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -491,7 +519,7 @@ static TcuLayout tcu_layout(int B, int H) {
   L.Kc = (H + 63) / 64;
   L.KS = (H + 15) / 16;
   L.Kp8 = (H + 7) / 8 * 8;
-  L.CP = 128 / nb < L.Kc ? 128 / nb : L.Kc;
+  L.CP = 128 / nb < L.Kc ? 128 / nb : L.Kc;     // K chunks per TMA request (<= 32 KB)
   L.NREQ = (L.Kc + L.CP - 1) / L.CP;
   L.smem = 1024 + (size_t)kURing * kUStage + (size_t)2 * nb * 384 + 256;
   size_t o = (size_t)2 * L.NTg * 128;

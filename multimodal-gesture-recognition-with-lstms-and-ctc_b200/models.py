@@ -149,7 +149,8 @@ class FusionNet(nn.Module):
             cur = torch.cuda.current_stream()
             if self._streams is None:
                 # (higher stream priority for the towers was measured: no gain)
-                self._streams = tuple(torch.cuda.Stream() for _ in range(4))
+                prio = int(os.environ.get("GR_TOWER_PRIO", "0"))
+                self._streams = tuple(torch.cuda.Stream(priority=prio) for _ in range(4))
             sa, sb, sc, sd = self._streams
             B = xa.shape[0]
             work = []

@@ -10,7 +10,7 @@ keep = os.environ.get("KEEP", "0") == "1"
 shapes = [tuple(int(v) for v in x.split("x")) for x in os.environ.get("SHAPES", "256x500,32x500").split(",")]
 T = 120
 names = ["tma_poll_done", "tma_issued", "mma_first_full", "mma_commit", "epi_tmem_full", "epi_ld_xpose", "epi_published", "epi_bar2",
-         "epi_red", "epi_P_in_regs", "epi_staged", "epi_iter_start", "epi_ld_waited", "epi_ld_arrived", "epi_stage1"]
+         "epi_red", "epi_P_in_regs", "epi_staged", "epi_iter_start", "epi_ld_waited", "epi_ld_arrived", "epi_stage1", "mma_pre_commit"]
 for (B, H) in shapes:
     gates = torch.randn(B * T, 8 * H, device=dev) * 0.5
     U = torch.randn(2, H, 4 * H, device=dev) / H ** 0.5
@@ -30,7 +30,7 @@ for (B, H) in shapes:
     lo, hi = 20, min(200, T * ntl - 4)
     for tau in range(ntl):
         sel = np.arange(lo + tau, hi, ntl)
-        st = tr[:, sel, :15].astype(np.int64)
+        st = tr[:, sel, :16].astype(np.int64)
         rel = st - st[:, :, 4:5]
         med = np.median(rel, axis=1)
         print(" tile %d:" % tau)
