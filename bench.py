@@ -31,24 +31,29 @@ LMAX = 35
 METRIC = "fusion BLSTM-CTC train seq/s"
 
 
+def _traffic_entry(kernel):
+    """Entry of `kernel` in the newest committed `ncu --set full` summary (profiles/rNN_traffic.json)."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        try:
+            d = json.load(open(path)).get(kernel)
+        except Exception:
+            d = None
+        if d is not None:
+            return d, name
+    return None, None
+
+
 def read_traffic_shape(kernel):
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        d = json.load(open(path)).get(kernel)
-        return None if d is None else "%s (profiles/r01_traffic.json)" % d["shape"]
-    except Exception:
-        return None
+    d, name = _traffic_entry(kernel)
+    return None if d is None else "%s (profiles/%s)" % (d["shape"], name)
 
 
 def read_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full`
-    capture (profiles/r01_traffic.json), or None."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        d = json.load(open(path)).get(kernel)
-        return None if d is None else d["dram_bytes"]
-    except Exception:
-        return None
+    capture, or None."""
+    d, _ = _traffic_entry(kernel)
+    return None if d is None else d["dram_bytes"]
 
 
 def read_peaks():
@@ -181,14 +186,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_seq = min(args.ref_batch, 16)   # bounded sample: ~5-10 s of host work per step
+    n_seq = args.ref_batch            # bounded sample (32 sequences, ~4 s of host work per step): the SAME sample the GPU arm's
+    #                                   `cpu_baseline` object times
     sec, threads = cpu_reference_step_time(n_seq, T_FRAMES, steps=args.steps, warmup=min(args.warmup, 1))
     v = n_seq / sec
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "seq/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "fusion BLSTM-CTC training step (multimodal.py), T=1000, C=22; CPU sample of "
-                                   "%d sequences per step" % n_seq, "global_batch": GLOBAL_BATCH, "seq_len": T_FRAMES},
+                                   "%d sequences per step (same sample as the GPU arm's cpu_baseline; 1 warm-up step)" % n_seq,
+                       "global_batch": GLOBAL_BATCH, "seq_len": T_FRAMES},
             "cpu_baseline": {"value": v, "unit": "seq/s", "cores": threads, "kind": "port",
                              "sample": "%d sequences x T=%d per step, %d steps, torch-CPU fp32 restatement "
                                        "(oracle/lstm_ref.py)" % (n_seq, T_FRAMES, args.steps)},
@@ -231,18 +238,18 @@ def ctc_microbench(dev, peak_gbs):
                          "algorithmic_bytes_per_frame": bytes_per_frame}}
 
 
-def ctc_sweep(dev, peak_gbs):
-    """BASELINE config 4 as written: B=1024, T in {100..2000}, L in {1,10,20,40} (capped at T/2), C=22, full and
-    ragged input lengths.  Opt-in (`--ctc-sweep`): ~60 kernel shapes."""
+def ctc_sweep(dev, peak_gbs, full=False):
+    """BASELINE config 4 as written: B=1024, T in {100..2000}, label length up to 40 (capped at T/2), C=22 and 44,
+    full and ragged input lengths.  Default: L in {10, 40} (56 shapes); `--ctc-sweep`: L in {1,10,20,40}."""
     import torch
     from mgr_b200 import ops
-    B, C = 1024, 22
+    B = 1024
     out = []
     rng = np.random.default_rng(3002)
-    for T in (100, 200, 400, 800, 1000, 1600, 2000):
-        g = torch.Generator().manual_seed(3001 + T)
-        probs = torch.softmax(torch.randn(B, T + 2, C, generator=g) * 2, -1).to(dev)
-        for L in (1, 10, 20, 40):
+    for C, T in [(c, t) for c in (22, 44) for t in (100, 200, 400, 800, 1000, 1600, 2000)]:
+        g = torch.Generator(device=dev).manual_seed(3001 + T + C)
+        probs = torch.softmax(torch.randn(B, T + 2, C, generator=g, device=dev) * 2, -1)
+        for L in ((1, 10, 20, 40) if full else (10, 40)):
             L = min(L, T // 2)
             labels = torch.tensor(rng.integers(0, C - 1, size=(B, L)), dtype=torch.int32, device=dev)
             ll = torch.full((B,), L, dtype=torch.int32, device=dev)
@@ -263,8 +270,9 @@ def ctc_sweep(dev, peak_gbs):
                 frames = int(il_np.sum())
                 bpf = 8 * C + 8 * (2 * L + 1)
                 ach = frames * bpf / (ms * 1e-3) / 1e9
-                out.append({"T": T, "L": L, "ragged": ragged, "ms": ms, "frames_per_s": frames / (ms * 1e-3),
-                            "achieved_GBps": ach, "frac": ach / peak_gbs})
+                out.append({"C": C, "T": T, "L": L, "ragged": ragged, "ms": round(ms, 4),
+                            "Gframes_per_s": round(frames / (ms * 1e-3) / 1e9, 3),
+                            "achieved_GBps": round(ach, 1), "frac": round(ach / peak_gbs, 3)})
         del probs
     return out
 
@@ -312,6 +320,101 @@ def decode_microbench(dev, peak_gbs):
                                           "unit": "GB/s", "frac": bytes_bp / (ms_bp * 1e-3) / 1e9 / peak_gbs}},
             "greedy": {"ms": ms_gr, "frames_per_s": frames / (ms_gr * 1e-3)},
             "beam100": {"ms": ms_bm, "frames_per_s": N * T / (ms_bm * 1e-3)}}
+
+
+def unimodal_leg(dev, hbm_peak, tc_peak, kind, steps=4, cpu=True):
+    """BASELINE config 2 (skeletal BLSTM-CTC TRAINING step, B=64, T=800: skeletal_lstm_ctc.py:296-394) and config 1
+    (speech BLSTM-CTC forward + ctc_batch_cost, B=16, T=400: speech_lstm_ctc_words.py) on one GPU, CUDA events; config 1
+    is the reference's CPU-runnable case, so the restated CPU path (oracle/lstm_ref.py) is timed beside it."""
+    import torch
+    import mgr_b200 as mgr
+    from mgr_b200 import _lib
+    names = ["gr_lstm_recurrence_fwd_f32", "gr_lstm_recurrence_bwd_f32", "gr_gemm_a32_f32", "gr_ctc_loss_grad_f32",
+             "gr_split_bf16_f32"]
+    if kind == "skeletal_train":
+        B, T, F, C, Lmax = 64, 800, 20, 22, 28
+        net = mgr.SkeletalNet().to(dev)
+        train = True
+    else:
+        B, T, F, C, Lmax = 16, 400, 39, 44, 20
+        net = mgr.SpeechNet().to(dev)
+        train = False
+    g = torch.Generator().manual_seed(1002 if train else 1001)
+    x = torch.randn(B, T, F, generator=g).to(dev)
+    rng = np.random.default_rng(1003)
+    labels = -np.ones((B, Lmax), dtype=np.float32)
+    ll = np.zeros((B, 1), dtype=np.int64)
+    for b in range(B):
+        L = int(rng.integers(1, Lmax + 1))
+        labels[b, :L] = rng.integers(0, C - 1, size=L)
+        ll[b, 0] = L
+    il = np.full((B, 1), T - 2, dtype=np.int64)
+    lab_t, il_t, ll_t = torch.tensor(labels), torch.tensor(il), torch.tensor(ll)
+    params = [p for p in net.parameters()]
+    opt = mgr.KerasAdam(params, lr=1e-4, clipvalue=0.5, decay=1e-5,
+                        maxnorm_params=[net.blstm_1.kernel, net.blstm_2.kernel], max_norm=3.0) if train else None
+    step_no = [0]
+
+    def step():
+        if train:
+            reg = net.sample_regularisers(B, T, seed=77, step=step_no[0], device=dev)
+            step_no[0] += 1
+            _, logits = net(x, reg)
+            loss = mgr.softmax_ctc(logits, lab_t, il_t, ll_t, check=False)
+            grads = torch.autograd.grad(loss.mean(), params)
+            opt.step(list(grads))
+        else:
+            with torch.no_grad():
+                y_pred, _ = net(x, None)
+                loss = mgr.ctc_lambda_func([y_pred, lab_t, il_t, ll_t])
+        return loss
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    _lib.kernel_timing_begin(names)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    kt = _lib.kernel_timing_end()
+    ms = e0.elapsed_time(e1) / steps
+    per_kernel = {k: {"ms_per_step": round(sum(v) / steps, 3), "launches_per_step": len(v) / steps} for k, v in kt.items()}
+    dom = max(per_kernel.items(), key=lambda kv: kv[1]["ms_per_step"])[0]
+    calls = _lib.kernel_timing_shapes.get(dom, [])
+    work = sum(calls) / max(1, len(calls))
+    avg_ms = sum(kt[dom]) / len(kt[dom])
+    if dom == "gr_gemm_a32_f32":
+        roof = {"kernel": dom, "bound": "tensor", "achieved": work / (avg_ms * 1e-3) / 1e12, "peak": tc_peak, "unit": "TFLOP/s"}
+    else:
+        roof = {"kernel": dom, "bound": "hbm", "achieved": work / (avg_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["avg_launch_ms"] = avg_ms
+    roof["share_of_step"] = per_kernel[dom]["ms_per_step"] / ms
+    roof["traffic"] = None
+    out = {"workload": ("skeletal BLSTM-CTC training step (skeletal_lstm_ctc.py), B=64 T=800 F=20 H=300 C=22, regularisers on"
+                        if train else "speech BLSTM-CTC forward + ctc_batch_cost (speech_lstm_ctc_words.py), B=16 T=400 F=39 "
+                                      "H=500 C=44, learning phase 0"),
+           "ms_per_step": ms, "seq_per_s": B / (ms * 1e-3), "loss_mean": float(loss.mean()), "kernels": per_kernel,
+           "roofline": roof}
+    if cpu and not train:
+        from oracle import lstm_ref
+        torch.set_num_threads(os.cpu_count() or 1)
+        rngw = np.random.default_rng(47)
+        t32 = lambda ws: [torch.tensor(w) for w in ws]
+        w1, w2 = t32(lstm_ref.init_blstm_weights(rngw, F, 500)), t32(lstm_ref.init_blstm_weights(rngw, 1000, 500))
+        wd = t32(lstm_ref.init_dense_weights(rngw, 1000, C))
+        xc = x.cpu()
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            pc, _ = lstm_ref.unimodal_forward(xc, w1, w2, wd)[:2]
+            lstm_ref.torch_ctc_lambda(pc, lab_t, il_t, ll_t)
+        sec = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": B / sec, "unit": "seq/s", "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": "the whole config (16 sequences x T=400), 1 pass, torch-CPU fp32 restatement, %.1f s" % sec}
+    return out
 
 
 def run_gpu(args):
@@ -493,15 +596,30 @@ def run_gpu(args):
                     "share_of_step": per_kernel[dom]["ms_per_step"] / serial_ms, "serial_step_ms": serial_ms,
                     "note": "durations from serial steps run right after the timed region; algorithmic flops 2MNK "
                             "(bf16x3 executes 3x that on the tensor pipe)"}
+    # ---- secondary fusion line at the reference's own maxlen (multimodal.py:222): T=1900, same schedule, 3 steps
+    t1900 = None
+    if not args.skip_ctc and T != 1900 and world == 1:
+        xa9, xs9, lab9, il9, ll9 = [t.to(dev) for t in synth_batch(lo, hi, 1900)]
+        tr9 = mgr.FusionTrainer(model, opt, seed=4321 + rank, global_batch=GLOBAL_BATCH, grad_hook=reduce_grads)
+        for _ in range(2):
+            tr9.step((xa9, xs9, lab9, il9, ll9), next_inputs=(xa9, xs9) if pipeline else None)
+        ms9 = timed(lambda: tr9.step((xa9, xs9, lab9, il9, ll9), next_inputs=(xa9, xs9) if pipeline else None), 3) / 3
+        tr9.close()
+        t1900 = {"seq_len": 1900, "ms_per_step": ms9, "value": GLOBAL_BATCH / (ms9 * 1e-3), "unit": "seq/s",
+                 "frames_per_s": GLOBAL_BATCH * 1900 / (ms9 * 1e-3)}
+        del xa9, xs9, tr9
+        torch.cuda.empty_cache()
     ctc = ctc_microbench(dev, hbm_peak) if not args.skip_ctc else None
-    if ctc is not None and args.ctc_sweep:
-        ctc["sweep"] = ctc_sweep(dev, hbm_peak)
+    if ctc is not None:
+        ctc["sweep"] = ctc_sweep(dev, hbm_peak, full=args.ctc_sweep)
     decode = decode_microbench(dev, hbm_peak) if not args.skip_ctc else None
+    config2 = unimodal_leg(dev, hbm_peak, tc_peak, "skeletal_train") if not args.skip_ctc else None
+    config1 = unimodal_leg(dev, hbm_peak, tc_peak, "speech_fwd", cpu=not args.skip_cpu) if not args.skip_ctc else None
     cpu = None
     if not args.skip_cpu:
-        sec, threads = cpu_reference_step_time(args.ref_batch, T, steps=1, warmup=0)
+        sec, threads = cpu_reference_step_time(args.ref_batch, T, steps=1, warmup=1)
         cpu = {"value": args.ref_batch / sec, "unit": "seq/s", "cores": threads, "kind": "port",
-               "sample": "%d sequences x T=%d, 1 step, torch-CPU fp32 restatement (oracle/lstm_ref.py), %.1f s"
+               "sample": "%d sequences x T=%d, 1 warm-up + 1 timed step, torch-CPU fp32 restatement (oracle/lstm_ref.py), %.1f s"
                          % (args.ref_batch, T, sec)}
     line = {"metric": METRIC, "value": value, "unit": "seq/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, args.min_warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -521,6 +639,7 @@ def run_gpu(args):
                             "device -> host read every step"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": per_kernel,
             "kernels_in_timed_region": overlapped,
+            "fusion_T1900": t1900, "config1_speech_fwd_loss": config1, "config2_skeletal_train": config2,
             "ctc": ctc, "decode": decode, "cpu_baseline": cpu, "loss_mean": float(torch.cat(losses).mean())}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -552,7 +671,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=32, help="sequences per CPU-baseline step (bounded sample)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-ctc", action="store_true")
-    ap.add_argument("--ctc-sweep", action="store_true", help="add the full BASELINE config-4 sweep to the 'ctc' object")
+    ap.add_argument("--ctc-sweep", action="store_true", help="all four label lengths in the config-4 sweep of the 'ctc' object (default: L = 10 and 40)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only")
     ap.add_argument("--min-warmup", type=int, default=3, help="profiling runs only (ncu launch lists)")
     args = ap.parse_args()
