@@ -289,6 +289,11 @@ size_t lstm_tcu_trace_offset(int B, int H);
 int lstm_fwd_tcu_launch(float* gates, const float* U, int B, int T, int H, float* y, float* cell, void* workspace,
                         cudaStream_t s);
 
+bool lstm_tcu_bwd_supported(int B, int H);
+size_t lstm_tcu_bwd_workspace_bytes(int B, int H);
+int lstm_bwd_tcu_launch(float* gates, const float* cell, const float* dy, const float* U, int B, int T, int H,
+                        void* workspace, cudaStream_t s);
+
 // register-resident-U path for narrow layers (lstm_small.cu)
 bool lstm_small_supported(int H);
 int lstm_small_run(bool bwd, float* gates, const float* U, int B, int T, int H, float* y, float* cell,
@@ -306,6 +311,13 @@ static bool use_tcu_path(int B, int H) {
   const char* d = getenv("GR_LSTM_TCU");           // default forward kernel for the wide layers; GR_LSTM_TCU=0: lstm_tc.cu
   if (d && d[0] == '0') return false;
   return lstm_tcu_supported(B, H);
+}
+static bool use_tcu_bwd_path(int B, int H) {
+  const char* e = getenv("GR_LSTM_IMPL");
+  if (e) return strcmp(e, "tcu") == 0 && lstm_tcu_bwd_supported(B, H);
+  const char* d = getenv("GR_LSTM_TCU");
+  if (d && d[0] == '0') return false;
+  return lstm_tcu_bwd_supported(B, H);
 }
 static bool use_tc_path(int B, int H) {
   const char* e = getenv("GR_LSTM_IMPL");
@@ -335,6 +347,8 @@ extern "C" int gr_lstm_workspace_bytes(int B, int H, size_t* bytes_out) {
   size_t tc = gr::lstm_tc_supported(B, H) ? gr::lstm_tc_workspace_bytes(B, H) : 0;
   size_t tcu = gr::lstm_tcu_supported(B, H) ? gr::lstm_tcu_workspace_bytes(B, H) : 0;
   if (tcu > tc) tc = tcu;
+  size_t tcub = gr::lstm_tcu_bwd_supported(B, H) ? gr::lstm_tcu_bwd_workspace_bytes(B, H) : 0;
+  if (tcub > tc) tc = tcub;
   *bytes_out = generic > tc ? generic : tc;
   return GR_OK;
 }
@@ -384,6 +398,8 @@ extern "C" int gr_lstm_recurrence_bwd_f32(float* gates, const float* cell, const
   if (workspace_bytes < need) return set_error(GR_EWORKSPACE, "lstm_bwd: workspace too small");
   if (use_small_path(H))
     return lstm_small_run(true, gates, U, B, T, H, nullptr, const_cast<float*>(cell), dy, static_cast<cudaStream_t>(stream));
+  if (use_tcu_bwd_path(B, H))
+    return lstm_bwd_tcu_launch(gates, cell, dy, U, B, T, H, workspace, static_cast<cudaStream_t>(stream));
   LstmBwdParams p;
   lstm_config(B, H, &p.HS, &p.UG, &p.Bp);
   if (2 * p.UG > num_sms()) return set_error(GR_EUNSUPPORTED, "lstm_bwd: H too large for the resident-U kernel");

@@ -103,6 +103,11 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t* w) {
                : "r"(taddr) : "memory");
 }
 
+__device__ __forceinline__ void tmem_st_zero_32x8(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z) : "memory");
+}
+
 // NB = batch rows per tile (16, 32, 64, 128); a CTA owns up to two tiles.
 template <int NB>
 __global__ void __launch_bounds__(kUThreads, 1)
@@ -496,6 +501,408 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
   }
 }
 
+// =================================================================================================
+// Backward through time on the same design.  dh_t = dy_t + dP_{t+1} U^T needs ALL 4H gate gradients of a batch row
+// (4x the forward exchange), and U^T for 16 units is [16 x 4H]: as the A operand it becomes 128 M-rows by splitting
+// K = 4H into its four gate blocks -- TMEM lane (unit u, bf16 part p, gate g) holds U[u, g*H + k], k < H (the same
+// 256 columns as forward).  The B operand of gate block g is the exchanged dP_g tile [NB rows x H]; the MMA's
+// disable-output-lane mask restricts each MMA to the 32 lanes of its gate block, so ONE accumulator D[128 x NB] ends
+// up with the partial sums (u, p, g) and the epilogue's shuffle butterfly ADDS the eight lanes of a unit instead
+// of transposing them.  Everything else is the forward kernel: L2 exchange + step counter, TMA ring, two interleaved
+// batch tiles, IO warp (loads gates_t / c_{t-1} / dy_t, stores dP_t in place of the gates).
+struct LstmTcuBwdParams {
+  uint8_t* dx;                 // exchange: [slab = (gate*Kc + chunk)*2 + part][(dir, parity, padded batch row)][64 bf16]
+  unsigned* counters;
+  const float* U;              // (2, H, 4H)
+  int B, T, H, Bpad, UGn, NTg, NSB, Kc, KS, CP, NREQ, NCH;
+};
+
+__device__ __forceinline__ void umma_ts_bf16_masked(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                                    uint32_t accum, uint32_t dis) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum), "r"(dis) : "memory");
+}
+__device__ __forceinline__ float dhsig_u(float s) { return (s > 0.f && s < 1.f) ? 0.2f : 0.f; }
+
+template <int NB>
+__global__ void __launch_bounds__(kUThreads, 1)
+lstm_bwd_tcu_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmG,
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmY, LstmTcuBwdParams p) {
+  constexpr int X = NB / 16;
+  constexpr bool STK = NB <= 32;
+  constexpr int DW = STK ? 2 * NB : NB;
+  constexpr int RING = NB == 128 ? 3 : 4;       // 128-row tiles: the input staging leaves room for three stages
+  constexpr uint32_t kIo = NB * 256;            // gates in / dP out: [4 gates][NB rows][16 units] fp32
+  constexpr uint32_t kYs = NB * 64;             // c_{t-1}, dy_t, c_T tiles: [NB rows][16 units] fp32
+  constexpr uint32_t kSlot = kIo + 2 * kYs;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  uint8_t* slots = ring + (size_t)RING * kUStage;         // 2 x { gates/dP, c_prev, dy }
+  uint8_t* cinit = slots + 2 * kSlot;                     // 2 x c at the first processed time step
+  uint64_t* full = reinterpret_cast<uint64_t*>(cinit + 2 * kYs);
+  uint64_t* empty = full + 4;
+  uint64_t* tmem_full = empty + 4;
+  uint64_t* in_full = tmem_full + 2;       // [2]  the slot's gates / c_prev / dy tiles landed
+  uint64_t* stage_ready = in_full + 2;     // [2]  256 epilogue threads staged the slot's dP tile
+  uint64_t* cinit_full = stage_ready + 2;  // [2]
+  uint64_t* ld_done = cinit_full + 2;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(ld_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ug = blockIdx.x % p.UGn;
+  const int sb = (blockIdx.x / p.UGn) % p.NSB;
+  const int dir = blockIdx.x / (p.UGn * p.NSB);
+  const int j0 = ug * kUUnits;
+  const int H = p.H, T = p.T;
+  const int ntl = min(2, p.NTg - 2 * sb);
+  const uint32_t stage_bytes = (uint32_t)p.CP * 2u * NB * 128u;
+  const bool need_empty = ntl * p.NREQ > RING;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmD)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmG)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY)) : "memory");
+    for (int s = 0; s < 4; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1); mbar_init(&in_full[s], 1); mbar_init(&stage_ready[s], kUEpi); mbar_init(&cinit_full[s], 1);
+    }
+    mbar_init(ld_done, kUEpi);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  // ---- one-time: rows of U -> TMEM.  Lane 32q + 16 part + 4 gate + ul holds U[unit 4q+ul][gate*H + k] (bf16 hi | lo)
+  if (warp >= 2 && warp < 6) {
+    const int q = warp & 3;
+    const int part = lane >> 4, gate = (lane >> 2) & 3, ul = lane & 3;
+    const int unit = j0 + 4 * q + ul;
+    const float* src = p.U + ((size_t)dir * H + unit) * 4 * H + (size_t)gate * H;
+    const bool live = unit < H;
+    for (int ks = 0; ks < p.KS; ++ks) {
+      uint32_t w[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k0 = ks * 16 + 4 * i;
+        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live && k0 < H) f = *reinterpret_cast<const float4*>(src + k0);   // H is a multiple of 4
+        const float e[4] = {f.x, f.y, f.z, f.w};
+        uint32_t pk[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(e[2 * c], e[2 * c + 1]);
+          uint32_t wv = *reinterpret_cast<const uint32_t*>(&hh);
+          if (part) {
+            const float f0 = __uint_as_float(wv << 16), f1 = __uint_as_float(wv & 0xffff0000u);
+            const __nv_bfloat162 ll = __floats2bfloat162_rn(e[2 * c] - f0, e[2 * c + 1] - f1);
+            wv = *reinterpret_cast<const uint32_t*>(&ll);
+          }
+          pk[c] = wv;
+        }
+        w[2 * i] = pk[0]; w[2 * i + 1] = pk[1];
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ks * 8);
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                   ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  // The accumulators are cleared by the epilogue warps (here and after every read) and EVERY MMA accumulates: with
+  // lane masks, a non-accumulating first MMA per gate block would depend on what the hardware does to disabled lanes.
+  if (warp >= 2 && warp < 10) {
+    const int q = warp & 3, hw = (warp - 2) >> 2;
+    for (int tau = 0; tau < 2; ++tau) {
+      const uint32_t taddr = tmem_base + kDBase + (uint32_t)(tau * DW + hw * (NB / 2)) + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int j = 0; j < X; ++j) {
+        tmem_st_zero_32x8(taddr + (uint32_t)(8 * j));
+        if (STK) tmem_st_zero_32x8(taddr + (uint32_t)(NB + 8 * j));
+      }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  if (warp == 0) {
+    // ---- dP stream of the previous backward step: (gate, chunk, part) slabs in slab order
+    int st = 0;
+    uint32_t ph = 0;
+    for (int sp = 1; sp < T; ++sp) {
+      for (int tau = 0; tau < ntl; ++tau) {
+        const int gt = 2 * sb + tau;
+        const unsigned* ctr = p.counters + (dir * p.NTg + gt) * 32;
+        const unsigned target = (unsigned)sp * p.UGn;
+        unsigned v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        } while (v < target);
+        asm volatile("fence.proxy.async;" ::: "memory");
+        const int row = (dir * 2 + ((sp + 1) & 1)) * p.Bpad + gt * NB;
+        for (int r = 0; r < p.NREQ; ++r) {
+          if (need_empty) mbar_wait(&empty[st], ph ^ 1);
+          if (elect_one_u()) {
+            mbar_expect_tx(&full[st], stage_bytes);
+            tma_load_3d_u(ring + (size_t)st * kUStage, &tmD, &full[st], 0, row, 2 * p.CP * r);
+          }
+          __syncwarp();
+          if (++st == RING) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issue: D[(u, p, g) x NB] += A[(u, p, g), k] x dP_g[rows, k]^T, lanes of the other gate blocks disabled
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(DW >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint64_t kSlab = (uint64_t)((NB * 128u) >> 4);
+    int st = 0;
+    uint32_t ph = 0;
+    for (int sp = 1; sp < T; ++sp) {
+      for (int tau = 0; tau < ntl; ++tau) {
+        const uint32_t dcol = tmem_base + kDBase + (uint32_t)(tau * DW);
+        const int m = (sp - 1) * ntl + tau;
+        if (m > 0) mbar_wait(ld_done, (uint32_t)((m - 1) & 1));
+        for (int r = 0; r < p.NREQ; ++r) {
+          mbar_wait(&full[st], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(ring + (size_t)st * kUStage);
+          if (elect_one_u()) {
+            int gc = r * p.CP;
+            const int gend = min(p.NCH, gc + p.CP);
+            int g = gc / p.Kc, c = gc - g * p.Kc;
+            uint64_t dB = make_sw128_desc(sa);
+            for (; gc < gend; ++gc) {
+              const uint32_t dis = ~((0xFu << (4 * g)) | (0xFu << (16 + 4 * g)));
+              const uint32_t a = tmem_base + (uint32_t)(c * 32);
+              const int nk = p.KS - 4 * c;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k < nk) {
+                  umma_ts_bf16_masked(dcol, a + (uint32_t)(8 * k), dB + (uint64_t)(2 * k), idesc, 1u, dis);
+                  if (!STK) umma_ts_bf16_masked(dcol, a + (uint32_t)(8 * k), dB + kSlab + (uint64_t)(2 * k), idesc, 1u, dis);
+                }
+              }
+              dB += 2 * kSlab;
+              if (++c == p.Kc) { c = 0; ++g; }
+            }
+            if (need_empty) umma_commit(&empty[st]);
+          }
+          __syncwarp();
+          if (++st == RING) { st = 0; ph ^= 1; }
+        }
+        if (elect_one_u()) umma_commit(&tmem_full[tau]);
+        __syncwarp();
+      }
+    }
+  } else if (warp < 10) {
+    // ---- epilogue: thread l of quadrant q holds lane (part, gate, ul); after the reducing butterfly it owns the cells
+    // (unit 4q + ul, column hw*NB/2 + 8*mm + 4*part + gam), mm < X -- the forward kernel's ownership
+    const int q = warp & 3;
+    const int hw = (warp - 2) >> 2;
+    const int part = lane >> 4, gam = (lane >> 2) & 3, ul = lane & 3;
+    const int et = threadIdx.x - 64;
+    const uint32_t uword = (uint32_t)ul * 4u;
+    uint32_t coff[X];
+#pragma unroll
+    for (int mm = 0; mm < X; ++mm) {
+      const uint32_t col = (uint32_t)(hw * (NB / 2) + 8 * mm + 4 * part + gam);
+      coff[mm] = sw64u(col, (uint32_t)q) + uword;
+    }
+    const size_t R = (size_t)4 * p.Bpad;
+    float c_cur[2][X], dcn[2][X];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int mm = 0; mm < X; ++mm) { c_cur[a][mm] = 0.f; dcn[a][mm] = 0.f; }
+
+    for (int sp = 0; sp < T; ++sp) {
+#pragma unroll
+      for (int tau = 0; tau < 2; ++tau) {
+        if (tau >= ntl) break;
+        const int n = sp * ntl + tau;
+        const int slot = n & 1;
+        uint8_t* io = slots + (size_t)slot * kSlot;
+        const uint8_t* cpt = io + kIo;
+        const uint8_t* dyt = cpt + kYs;
+        mbar_wait(&in_full[slot], (uint32_t)(n >> 1) & 1u);
+        if (sp == 0) {
+          mbar_wait(&cinit_full[tau], 0u);
+#pragma unroll
+          for (int mm = 0; mm < X; ++mm) c_cur[tau][mm] = *reinterpret_cast<const float*>(cinit + tau * kYs + coff[mm]);
+        }
+        float gt4[X][4], cpv[X], dh[X];
+#pragma unroll
+        for (int mm = 0; mm < X; ++mm) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) gt4[mm][g] = *reinterpret_cast<const float*>(io + g * kYs + coff[mm]);
+          cpv[mm] = *reinterpret_cast<const float*>(cpt + coff[mm]);
+          dh[mm] = *reinterpret_cast<const float*>(dyt + coff[mm]);
+        }
+        if (sp > 0) {
+          mbar_wait(&tmem_full[tau], (uint32_t)((sp - 1) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          uint32_t v[8 * X];
+          const uint32_t taddr = tmem_base + kDBase + (uint32_t)(tau * DW + hw * (NB / 2)) + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+          for (int j = 0; j < X; ++j) tmem_ld_32x8(taddr + (uint32_t)(8 * j), v + 8 * j);
+          if constexpr (STK) {
+            uint32_t v2[8 * X];
+#pragma unroll
+            for (int j = 0; j < X; ++j) tmem_ld_32x8(taddr + (uint32_t)(NB + 8 * j), v2 + 8 * j);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 8 * X; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < X; ++j) {          // clear the accumulator for the tile's next step
+            tmem_st_zero_32x8(taddr + (uint32_t)(8 * j));
+            if (STK) tmem_st_zero_32x8(taddr + (uint32_t)(NB + 8 * j));
+          }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive_u(ld_done);
+          // reducing butterfly over the unit's eight lanes (part, gate): each stage keeps half of the columns and adds
+          // the partner's values for them
+          const bool bp = part != 0, b1 = (gam & 2) != 0, b0 = (gam & 1) != 0;
+          float w4[4 * X];
+#pragma unroll
+          for (int mm = 0; mm < X; ++mm)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float keep = __uint_as_float(bp ? v[8 * mm + 4 + k] : v[8 * mm + k]);
+              const float send = __uint_as_float(bp ? v[8 * mm + k] : v[8 * mm + 4 + k]);
+              w4[4 * mm + k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+          float w2[2 * X];
+#pragma unroll
+          for (int mm = 0; mm < X; ++mm)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const float keep = b1 ? w4[4 * mm + 2 + k] : w4[4 * mm + k];
+              const float send = b1 ? w4[4 * mm + k] : w4[4 * mm + 2 + k];
+              w2[2 * mm + k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+          for (int mm = 0; mm < X; ++mm) {
+            const float keep = b0 ? w2[2 * mm + 1] : w2[2 * mm];
+            const float send = b0 ? w2[2 * mm] : w2[2 * mm + 1];
+            dh[mm] += keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+        }
+#pragma unroll
+        for (int mm = 0; mm < X; ++mm) {
+          const float gi = gt4[mm][0], gf = gt4[mm][1], gg = gt4[mm][2], go = gt4[mm][3];
+          const float tc = tanh_u(c_cur[tau][mm]);
+          const float dc = dcn[tau][mm] + dh[mm] * go * (1.f - tc * tc);
+          const float d_o = dh[mm] * tc * dhsig_u(go);
+          const float d_i = dc * gg * dhsig_u(gi);
+          const float d_g = dc * gi * (1.f - gg * gg);
+          const float d_f = dc * cpv[mm] * dhsig_u(gf);
+          dcn[tau][mm] = dc * gf;
+          c_cur[tau][mm] = cpv[mm];
+          *reinterpret_cast<float*>(io + 0 * kYs + coff[mm]) = d_i;
+          *reinterpret_cast<float*>(io + 1 * kYs + coff[mm]) = d_f;
+          *reinterpret_cast<float*>(io + 2 * kYs + coff[mm]) = d_g;
+          *reinterpret_cast<float*>(io + 3 * kYs + coff[mm]) = d_o;
+        }
+        if (sp + 1 < T) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");    // dP tile staged
+          // publish dP_t as bf16 hi / lo: one 32-byte sector per (row, gate, part)
+          for (int it = et; it < 8 * NB; it += kUEpi) {
+            const int ppart = it & 1, pg = (it >> 1) & 3, prow = it >> 3;
+            float hv[16];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              const float4 f = *reinterpret_cast<const float4*>(io + pg * kYs + sw64u((uint32_t)prow, (uint32_t)ch));
+              hv[4 * ch] = f.x; hv[4 * ch + 1] = f.y; hv[4 * ch + 2] = f.z; hv[4 * ch + 3] = f.w;
+            }
+            uint32_t w[8];
+#pragma unroll
+            for (int u = 0; u < 16; u += 2) {
+              const __nv_bfloat162 hh = __floats2bfloat162_rn(hv[u], hv[u + 1]);
+              uint32_t wv = *reinterpret_cast<const uint32_t*>(&hh);
+              if (ppart) {
+                const float f0 = __uint_as_float(wv << 16), f1 = __uint_as_float(wv & 0xffff0000u);
+                const __nv_bfloat162 ll = __floats2bfloat162_rn(hv[u] - f0, hv[u + 1] - f1);
+                wv = *reinterpret_cast<const uint32_t*>(&ll);
+              }
+              w[u >> 1] = wv;
+            }
+            const size_t rowR = (size_t)(dir * 2 + (sp & 1)) * p.Bpad + (size_t)(2 * sb + tau) * NB + prow;
+            const size_t slab = ((size_t)pg * p.Kc + (size_t)(j0 >> 6)) * 2 + ppart;
+            uint8_t* dst = p.dx + (slab * R + rowR) * 128 + (size_t)(j0 & 63) * 2;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(dst + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (et == 0) {
+            unsigned* ctr = p.counters + (dir * p.NTg + 2 * sb + tau) * 32;
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive_u(&stage_ready[slot]);
+      }
+    }
+  } else if (warp == 10) {
+    // ---- IO warp.  Backward step sp differentiates forward step s = T-1-sp at time t (forward-previous time tp; a tp
+    // outside [0, T) makes the whole c_prev box out of bounds: TMA fills it with zeros = the initial cell state)
+    if (lane == 0) {
+      const int total = T * ntl;
+      for (int tau = 0; tau < ntl; ++tau) {
+        mbar_expect_tx(&cinit_full[tau], kYs);
+        tma_load_4d_u(cinit + tau * kYs, &tmC, &cinit_full[tau], j0, (2 * sb + tau) * NB, dir == 0 ? T - 1 : 0, dir);
+      }
+      auto load_inputs = [&](int slot, int sp, int tau) {
+        uint8_t* io = slots + (size_t)slot * kSlot;
+        const int t = dir == 0 ? T - 1 - sp : sp;
+        const int tp = dir == 0 ? t - 1 : t + 1;
+        const int b0 = (2 * sb + tau) * NB;
+        mbar_expect_tx(&in_full[slot], kIo + 2 * kYs);
+        tma_load_4d_u(io, &tmG, &in_full[slot], j0, b0, t, dir * 4);
+        tma_load_4d_u(io + kIo, &tmC, &in_full[slot], j0, b0, tp, dir);
+        tma_load_4d_u(io + kIo + kYs, &tmY, &in_full[slot], j0, b0, t, dir);
+      };
+      for (int n = 0; n < min(2, total); ++n) load_inputs(n & 1, n / ntl, n % ntl);
+      int sp = 0, tau = 0;
+      for (int n = 0; n < total; ++n) {
+        const int slot = n & 1;
+        uint8_t* io = slots + (size_t)slot * kSlot;
+        const int t = dir == 0 ? T - 1 - sp : sp;
+        mbar_wait(&stage_ready[slot], (uint32_t)(n >> 1) & 1u);
+        tma_store_4d_u(&tmG, io, j0, (2 * sb + tau) * NB, t, dir * 4);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        int sp2 = sp, tau2 = tau;
+        for (int a = 0; a < 2; ++a) { if (++tau2 == ntl) { tau2 = 0; ++sp2; } }
+        if (sp2 < T) load_inputs(slot, sp2, tau2);
+        if (++tau == ntl) { tau = 0; ++sp; }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 int split_bf16_t_launch(const float* x, int R, int K, int ldx, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_out,
                         cudaStream_t s);
 
@@ -595,6 +1002,81 @@ int lstm_fwd_tcu_launch(float* gates, const float* U, int B, int T, int H, float
     case 32: return go(lstm_fwd_tcu_kernel<32>);
     case 64: return go(lstm_fwd_tcu_kernel<64>);
     default: return go(lstm_fwd_tcu_kernel<128>);
+  }
+}
+
+
+struct TcuBwdLayout {
+  int NB, NTg, NSB, Bpad, UGn, Kc, KS, CP, NREQ, NCH;
+  size_t off_dx, total, smem;
+};
+static TcuBwdLayout tcu_bwd_layout(int B, int H) {
+  TcuBwdLayout L;
+  int nb = 16;
+  while (nb < 128 && 2 * nb < B) nb *= 2;
+  L.NB = nb;
+  L.NTg = (B + nb - 1) / nb;
+  L.NSB = (L.NTg + 1) / 2;
+  L.Bpad = L.NTg * nb;
+  L.UGn = (H + kUUnits - 1) / kUUnits;
+  L.Kc = (H + 63) / 64;
+  L.KS = (H + 15) / 16;
+  L.NCH = 4 * L.Kc;
+  L.CP = 128 / nb < L.NCH ? 128 / nb : L.NCH;
+  L.NREQ = (L.NCH + L.CP - 1) / L.CP;
+  const int ring = nb == 128 ? 3 : 4;
+  L.smem = 1024 + (size_t)ring * kUStage + (size_t)2 * nb * 384 + (size_t)2 * nb * 64 + 256;
+  size_t o = (size_t)2 * L.NTg * 128;
+  o = (o + 1023) & ~(size_t)1023;
+  L.off_dx = o; o += (size_t)2 * L.NCH * 4 * L.Bpad * 128;
+  L.total = o + 256;
+  return L;
+}
+
+size_t lstm_tcu_bwd_workspace_bytes(int B, int H) { return tcu_bwd_layout(B, H).total; }
+
+bool lstm_tcu_bwd_supported(int B, int H) {
+  if (H % 4 != 0 || H < 32 || H > 512) return false;
+  TcuBwdLayout L = tcu_bwd_layout(B, H);
+  return 2 * L.NSB * L.UGn <= num_sms();
+}
+
+int lstm_bwd_tcu_launch(float* gates, const float* cell, const float* dy, const float* U, int B, int T, int H,
+                        void* workspace, cudaStream_t s) {
+  TcuBwdLayout L = tcu_bwd_layout(B, H);
+  char* w = static_cast<char*>(workspace);
+  LstmTcuBwdParams p;
+  p.dx = reinterpret_cast<uint8_t*>(w + L.off_dx);
+  p.counters = reinterpret_cast<unsigned*>(w);
+  p.U = U;
+  p.B = B; p.T = T; p.H = H; p.Bpad = L.Bpad; p.UGn = L.UGn; p.NTg = L.NTg; p.NSB = L.NSB; p.Kc = L.Kc; p.KS = L.KS;
+  p.CP = L.CP; p.NREQ = L.NREQ; p.NCH = L.NCH;
+  GR_CUDA(cudaMemsetAsync(w, 0, L.total - 256, s));   // counters + exchange buffer (K padding and padded rows stay zero)
+  CUtensorMap tD, tG, tC, tY;
+  int rc;
+  {
+    const cuuint64_t R = (cuuint64_t)4 * L.Bpad;
+    const cuuint64_t dims[3] = {64, R, (cuuint64_t)2 * L.NCH};
+    const cuuint64_t strides[2] = {128, R * 128};
+    const cuuint32_t box[3] = {64, (cuuint32_t)L.NB, (cuuint32_t)(2 * L.CP)};
+    if ((rc = make_map_nd(&tD, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p.dx, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) != GR_OK)
+      return rc;
+  }
+  if ((rc = make_io_map_u(&tG, gates, B, T, H, 8, L.NB, 4)) != GR_OK) return rc;
+  if ((rc = make_io_map_u(&tC, cell, B, T, H, 2, L.NB, 1)) != GR_OK) return rc;
+  if ((rc = make_io_map_u(&tY, dy, B, T, H, 2, L.NB, 1)) != GR_OK) return rc;
+  void* args[] = {&tD, &tG, &tC, &tY, &p};
+  const dim3 grid(2 * L.NSB * L.UGn), block(kUThreads);
+  auto go = [&](auto kern) -> int {
+    GR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+    GR_CUDA(cudaLaunchCooperativeKernel((void*)kern, grid, block, args, L.smem, s));
+    return GR_OK;
+  };
+  switch (L.NB) {
+    case 16: return go(lstm_bwd_tcu_kernel<16>);
+    case 32: return go(lstm_bwd_tcu_kernel<32>);
+    case 64: return go(lstm_bwd_tcu_kernel<64>);
+    default: return go(lstm_bwd_tcu_kernel<128>);
   }
 }
 

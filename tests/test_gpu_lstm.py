@@ -52,7 +52,10 @@ def _ref(x, W, U, b, masks, dy):
 
 @pytest.mark.parametrize("B,T,F,H,masked", [(4, 6, 8, 8, False), (5, 17, 20, 12, False), (3, 9, 39, 20, True),
                                             (16, 12, 64, 100, False), (7, 10, 24, 300, False),
-                                            (6, 8, 40, 500, True), (32, 5, 16, 36, False)])
+                                            (6, 8, 40, 500, True), (32, 5, 16, 36, False),
+                                            # BASELINE config-2 / config-1 layer shapes (short T): both tcgen05 recurrence
+                                            # kernels (forward and BPTT with U in tensor memory), two batch tiles per CTA
+                                            (64, 20, 20, 300, True), (16, 14, 39, 500, False), (70, 9, 24, 300, False)])
 def test_blstm_forward_backward(cuda, B, T, F, H, masked):
     import mgr_b200 as mgr
     for attempt in range(20):  # deterministic search for a well-conditioned seed (see _gate_margin)
@@ -201,3 +204,23 @@ def test_bench_size_recurrence_against_fp64(cuda, monkeypatch, impl):
         if keep:
             assert np.abs(cell.cpu().numpy() - c_ref).max() <= 5e-4
             assert np.abs(g.cpu().numpy().reshape(B, T, 8 * H) - g_ref).max() <= 2e-4
+
+
+@pytest.mark.parametrize("B,T,H", [(64, 40, 300), (256, 16, 500)])
+def test_tensor_core_bptt_matches_generic_and_is_deterministic(cuda, monkeypatch, B, T, H):
+    """lstm_bwd_tcu_kernel (masked TS-mode MMAs, reducing butterfly) vs the generic fp32 BPTT kernel on the same saved
+    forward state, at the config-2 layer size and at the bench batch; bit-identical repeats."""
+    from mgr_b200 import ops
+    g = torch.Generator().manual_seed(B + H)
+    P = (torch.randn(B * T, 8 * H, generator=g) * 0.7).to(cuda)
+    U = (torch.randn(2, H, 4 * H, generator=g) / H ** 0.5).to(cuda)
+    dy = (torch.randn(B, T, 2 * H, generator=g) * 0.1).to(cuda)
+    gates = P.clone()
+    _, cell = ops.lstm_recurrence_fwd(gates, U, B, T, H, keep_cell=True)
+    monkeypatch.setenv("GR_LSTM_IMPL", "generic")
+    d_gen = ops.lstm_recurrence_bwd(gates.clone(), cell, dy, U, B, T, H).clone()
+    monkeypatch.setenv("GR_LSTM_IMPL", "tcu")
+    d_tc = ops.lstm_recurrence_bwd(gates.clone(), cell, dy, U, B, T, H).clone()
+    d_tc2 = ops.lstm_recurrence_bwd(gates.clone(), cell, dy, U, B, T, H).clone()
+    assert torch.equal(d_tc, d_tc2)
+    assert (d_tc - d_gen).abs().max().item() <= 1e-4 * d_gen.abs().max().item()
