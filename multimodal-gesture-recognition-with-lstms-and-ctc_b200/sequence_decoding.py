@@ -63,13 +63,21 @@ def decode_batch_speech(pred_out, f_list, map_gest, threshold=0.75, mlf_path="ct
 
 
 def ctc_decode(y_pred, input_length, greedy=True, beam_width=100, top_paths=1, merge_repeated=True, eps=1e-8):
-    """Keras `K.ctc_decode`: returns ([decoded (N, Tmax) int64 padded -1] * top_paths, log_prob (N, top_paths)).
-    merge_repeated defaults to TF 1.12's ctc_beam_search_decoder default (Keras 2.1.4 does not pass it)."""
+    """Keras `K.ctc_decode`: returns ([decoded (N, max decoded length) int64 padded -1] * top_paths,
+    log_prob (N, top_paths)) -- the dense form of the SparseTensor Keras builds, so the width is the longest decoded
+    sequence, not T.  merge_repeated defaults to TF 1.12's ctc_beam_search_decoder default (Keras 2.1.4 does not pass it).
+    Beam log_prob: every frame is fully normalised (log_softmax of log(p + eps)) before the search; the pinned TF
+    1.12 kernel is believed to subtract only the per-frame maximum, which shifts log_prob by sum_t(lse_t - max_t) and
+    cannot change the decoded labels (a per-frame constant) -- DESIGN.md section 2."""
     p = _to_device(y_pred)
     N = p.shape[0]
     sl = torch.as_tensor(input_length).reshape(N).to(device=p.device, dtype=torch.int32)
+
+    def trim(ids2d, lens1d):
+        w = max(int(lens1d.max().item()) if lens1d.numel() else 0, 1)
+        return ids2d[:, :w].to(torch.int64).contiguous()
     if greedy:
         ids, lens, score = ops.greedy(p, sl, eps)
-        return [ids.to(torch.int64)], score.reshape(N, 1)
+        return [trim(ids, lens)], score.reshape(N, 1)
     ids, lens, logp = ops.beam(p, sl, beam_width, top_paths, merge_repeated, eps)
-    return [ids[:, k].to(torch.int64) for k in range(top_paths)], logp
+    return [trim(ids[:, k], lens[:, k] if lens.dim() == 2 else lens) for k in range(top_paths)], logp

@@ -20,6 +20,20 @@ elif what == "lstm_tc":
     U = torch.randn(2, H, 4 * H, device=dev) / H ** 0.5
     for _ in range(2):
         ops.lstm_recurrence_fwd(gates.clone(), U, B, T, H, keep_cell=False)
+elif what == "lstm_tcu":       # the default forward recurrence (lstm_tcu.cu): speech tower layer, inference
+    B, T, H = 256, 1000, 500
+    gates = torch.randn(B * T, 8 * H, device=dev) * 0.5
+    U = torch.randn(2, H, 4 * H, device=dev) / H ** 0.5
+    for _ in range(2):
+        ops.lstm_recurrence_fwd(gates.clone(), U, B, T, H, keep_cell=False)
+elif what == "lstm_tcu_bwd":   # tensor-core BPTT at the config-2 layer size
+    B, T, H = 64, 800, 300
+    gates = torch.randn(B * T, 8 * H, device=dev) * 0.5
+    U = torch.randn(2, H, 4 * H, device=dev) / H ** 0.5
+    dy = torch.randn(B, T, 2 * H, device=dev) * 0.1
+    y, cell = ops.lstm_recurrence_fwd(gates, U, B, T, H, keep_cell=True)
+    for _ in range(2):
+        ops.lstm_recurrence_bwd(gates.clone(), cell, dy, U, B, T, H)
 elif what == "gemm":
     M, N, K = 65536, 4000, 1000
     x = torch.randn(M, K, device=dev); W = torch.randn(K, N, device=dev) * 0.05

@@ -54,6 +54,8 @@ def test_greedy_matches_oracle(cuda):
     sl = rng.integers(T // 2, T + 1, size=N)
     dec, score = mgr.ctc_decode(s, sl, greedy=True)
     dec = dec[0].cpu().numpy()
+    # dense form of Keras' SparseTensor: as wide as the longest decoded sequence (not T)
+    assert dec.shape[1] == max(1, max(len(decode_ref.ctc_greedy(s[j], int(sl[j]))[0]) for j in range(N)))
     for j in range(N):
         ref, ref_score = decode_ref.ctc_greedy(s[j], int(sl[j]))
         got = [int(v) for v in dec[j] if v >= 0]
