@@ -11,11 +11,9 @@ then the backward three; gate order i,f,c,o; for `Dense`: kernel, bias -- under 
 gives them (`bidirectional_1/forward_blstm_1/kernel:0`, ...), which is also how `load_weights` matches:
 by position, names are informative (Keras' topological loading).
 
-Container: `.npz` (NumPy).  The reference's `.h5` files are HDF5; h5py is not part of this image and an
-HDF5 reader that could not be checked against a single real Keras file would be guesswork, so the bridge
-is a ten-line conversion on any machine that has h5py: it walks
-`f.attrs['layer_names']` / `g.attrs['weight_names']` and writes the arrays in that order into the `.npz`
-this module reads.
+Containers: `.h5` / `.hdf5` -- the reference's own format, through the pure-Python reader / writer of
+`keras_h5.py` (classic HDF5 as h5py writes it for Keras 2.1.4: `layer_names` / `weight_names` attributes, one
+dataset per weight) -- and `.npz` (NumPy), which `scripts/h5_to_npz.py` also produces on a machine with h5py.
 """
 import json
 from collections import OrderedDict
@@ -87,18 +85,34 @@ def _assign(model, arrays):
         raise ValueError("load_weights: %d arrays left over" % len(rest))
 
 
+def _is_h5(path):
+    return str(path).lower().endswith((".h5", ".hdf5"))
+
+
 def save_weights(model, path):
-    """`model.save_weights(path)`: one array per Keras weight, keys 'NNN|<keras weight name>' (NNN keeps the order)."""
+    """`model.save_weights(path)`.  `.h5`: the Keras 2.1.4 HDF5 tree (keras_h5.write_keras_weights); otherwise `.npz`,
+    one array per Keras weight, keys 'NNN|<keras weight name>' (NNN keeps the order)."""
+    if _is_h5(path):
+        from . import keras_h5
+        table = weight_table(model)
+        keras_h5.write_keras_weights(path, [(lname, entries) for lname, entries in table.items()])
+        return [n for entries in table.values() for n, _ in entries]
     flat = [(n, a) for entries in weight_table(model).values() for n, a in entries]
     np.savez(path, **{"%03d|%s" % (i, n): a for i, (n, a) in enumerate(flat)})
     return [n for n, _ in flat]
 
 
 def load_weights(model, path):
-    """`model.load_weights(path)`: topological (positional) matching with shape checks, like Keras."""
-    with np.load(path) as z:
-        keys = sorted(z.files, key=lambda k: int(k.split("|", 1)[0]))
-        arrays = [z[k] for k in keys]
+    """`model.load_weights(path)`: topological (positional) matching with shape checks, like Keras.  `.h5` files are read
+    in `layer_names` / `weight_names` order (what load_weights_from_hdf5_group iterates)."""
+    if _is_h5(path):
+        from . import keras_h5
+        pairs = [(n, a) for _, ws in keras_h5.read_keras_weights(path) for n, a in ws]
+        keys, arrays = [n for n, _ in pairs], [np.asarray(a, dtype=np.float32) for _, a in pairs]
+    else:
+        with np.load(path) as z:
+            keys = sorted(z.files, key=lambda k: int(k.split("|", 1)[0]))
+            arrays = [z[k] for k in keys]
     want = [a for entries in weight_table(model).values() for _, a in entries]
     if len(arrays) != len(want):
         raise ValueError("load_weights: file holds %d arrays, the model needs %d" % (len(arrays), len(want)))
