@@ -200,6 +200,18 @@ int gr_adam_step_f32(float* param, const float* grad, float* m, float* v, size_t
                      int cols, float lr, float beta1, float beta2, float eps, float decay,
                      float clipvalue, float max_norm, int64_t step, void* stream);
 
+/* Multi-tensor optimiser epilogue (one launch over the flat gradient bucket behind the all-reduce; the reference's
+ * optimiser updates every trainable weight in one session.run: multimodal.py:206-208).  `srcs` / `params` / `sizes`
+ * are HOST arrays of n_tensors (<= GR_MT_MAX) device pointers / element counts; flat buffers hold the tensors back to
+ * back in that order.  gr_pack_f32: flat <- concat(srcs).  gr_adam_flat_f32: clipvalue + Keras Adam (lr decay as in
+ * gr_adam_step_f32) on every tensor.  gr_maxnorm_f32: kernel_constraint=maxnorm (multimodal.py:165) on one (rows, cols). */
+#define GR_MT_MAX 8
+int gr_pack_f32(const float* const* srcs, const size_t* sizes, int n_tensors, float* flat, void* stream);
+int gr_adam_flat_f32(float* const* params, const size_t* sizes, int n_tensors, const float* flat_grad,
+                     float* flat_m, float* flat_v, float lr, float beta1, float beta2, float eps,
+                     float decay, float clipvalue, int64_t step, void* stream);
+int gr_maxnorm_f32(float* w, int rows, int cols, float max_norm, void* stream);
+
 /* Philox-based regularisers (on-device RNG; the reference's GaussianNoise / Dropout /
  * LSTM input-dropout masks).  out[i] = keep ? 1/(1-p) : 0 ; noise[i] ~ N(0, stddev). */
 int gr_dropout_mask_f32(float* out, size_t n, float p, uint64_t seed, uint64_t offset,

@@ -57,6 +57,10 @@ _SIGNATURES = {
     "gr_concat2_f32": ([_P, c_int, _P, c_int, _P, c_size_t, _P], c_int),
     "gr_adam_step_f32": ([_P, _P, _P, _P, c_size_t, c_int, c_int, c_float, c_float, c_float, c_float, c_float,
                           c_float, c_float, c_int64, _P], c_int),
+    "gr_pack_f32": ([_P, _P, c_int, _P, _P], c_int),
+    "gr_adam_flat_f32": ([_P, _P, c_int, _P, _P, _P, c_float, c_float, c_float, c_float, c_float, c_float, c_int64, _P],
+                         c_int),
+    "gr_maxnorm_f32": ([_P, c_int, c_int, c_float, _P], c_int),
     "gr_dropout_mask_f32": ([_P, c_size_t, c_float, c_uint64, c_uint64, _P], c_int),
     "gr_gaussian_noise_f32": ([_P, c_size_t, c_float, c_uint64, c_uint64, _P], c_int),
 }

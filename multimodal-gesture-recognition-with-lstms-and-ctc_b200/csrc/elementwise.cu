@@ -443,6 +443,89 @@ extern "C" int gr_adam_step_f32(float* param, const float* grad, float* m, float
   return GR_OK;
 }
 
+// ------------------------------------------------------------------ multi-tensor optimiser epilogue
+// One launch over the flat gradient bucket (behind the all-reduce): clipvalue + Adam for every trainable tensor, the
+// parameter pointers travelling in the kernel arguments (multimodal.py:206-208: five tensors in the fusion model).
+namespace gr {
+struct MtTable {
+  float* ptr[GR_MT_MAX];
+  unsigned long long off[GR_MT_MAX + 1];   // element offsets of the tensors inside the flat buffers
+  int n;
+};
+__global__ void pack_kernel(MtTable tab, float* __restrict__ flat) {
+  const size_t total = tab.off[tab.n];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int t = 0;
+    while (t + 1 < tab.n && i >= tab.off[t + 1]) ++t;
+    flat[i] = tab.ptr[t][i - tab.off[t]];
+  }
+}
+__global__ void adam_flat_kernel(MtTable tab, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                 float lr_t, float beta1, float beta2, float eps, float clip) {
+  const size_t total = tab.off[tab.n];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int t = 0;
+    while (t + 1 < tab.n && i >= tab.off[t + 1]) ++t;
+    float gi = g[i];
+    if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float* p = tab.ptr[t] + (i - tab.off[t]);
+    *p = *p - lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+static int fill_table(MtTable* tab, float* const* ptrs, const size_t* sizes, int n) {
+  if (!ptrs || !sizes || n <= 0 || n > GR_MT_MAX) return set_error(GR_EINVAL, "multi-tensor: 1..GR_MT_MAX tensors");
+  tab->n = n;
+  tab->off[0] = 0;
+  for (int t = 0; t < n; ++t) {
+    if (!ptrs[t] || sizes[t] == 0) return set_error(GR_EINVAL, "multi-tensor: null or empty tensor");
+    tab->ptr[t] = ptrs[t];
+    tab->off[t + 1] = tab->off[t] + sizes[t];
+  }
+  return GR_OK;
+}
+}  // namespace gr
+
+extern "C" int gr_pack_f32(const float* const* srcs, const size_t* sizes, int n_tensors, float* flat, void* stream) {
+  using namespace gr;
+  MtTable tab;
+  int rc = fill_table(&tab, const_cast<float* const*>(reinterpret_cast<const float* const*>(srcs)), sizes, n_tensors);
+  if (rc != GR_OK) return rc;
+  if (!flat) return set_error(GR_EINVAL, "pack: null pointer");
+  pack_kernel<<<grid_for(tab.off[tab.n]), 256, 0, static_cast<cudaStream_t>(stream)>>>(tab, flat);
+  GR_CHECK_LAUNCH("pack_kernel");
+  return GR_OK;
+}
+
+extern "C" int gr_adam_flat_f32(float* const* params, const size_t* sizes, int n_tensors, const float* flat_grad,
+                                float* flat_m, float* flat_v, float lr, float beta1, float beta2, float eps, float decay,
+                                float clipvalue, int64_t step, void* stream) {
+  using namespace gr;
+  MtTable tab;
+  int rc = fill_table(&tab, params, sizes, n_tensors);
+  if (rc != GR_OK) return rc;
+  if (!flat_grad || !flat_m || !flat_v) return set_error(GR_EINVAL, "adam_flat: null pointer");
+  double lr_d = lr;                       // Keras 2.1.4 Adam.get_updates (see gr_adam_step_f32)
+  if (decay > 0.f) lr_d *= 1.0 / (1.0 + (double)decay * (double)step);
+  const double t = (double)step + 1.0;
+  const float lr_t = (float)(lr_d * sqrt(1.0 - pow((double)beta2, t)) / (1.0 - pow((double)beta1, t)));
+  adam_flat_kernel<<<grid_for(tab.off[tab.n]), 256, 0, static_cast<cudaStream_t>(stream)>>>(tab, flat_grad, flat_m, flat_v, lr_t,
+                                                                                            beta1, beta2, eps, clipvalue);
+  GR_CHECK_LAUNCH("adam_flat_kernel");
+  return GR_OK;
+}
+
+extern "C" int gr_maxnorm_f32(float* w, int rows, int cols, float max_norm, void* stream) {
+  using namespace gr;
+  if (!w || rows <= 0 || cols <= 0 || max_norm <= 0.f) return set_error(GR_EINVAL, "maxnorm: bad argument");
+  maxnorm_kernel<<<(cols + 31) / 32, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(w, rows, cols, max_norm);
+  GR_CHECK_LAUNCH("maxnorm_kernel");
+  return GR_OK;
+}
+
 extern "C" int gr_dropout_mask_f32(float* out, size_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
   using namespace gr;
   if (!out || n == 0 || p < 0.f || p >= 1.f) return set_error(GR_EINVAL, "dropout_mask: bad argument");

@@ -252,15 +252,35 @@ class KerasAdam:
         self.lr, self.beta1, self.beta2, self.eps, self.decay, self.clipvalue = lr, beta1, beta2, eps, decay, clipvalue
         self.maxnorm_ids = {id(p) for p in maxnorm_params}
         self.max_norm = max_norm
-        self.m = [torch.zeros_like(p) for p in self.params]
-        self.v = [torch.zeros_like(p) for p in self.params]
+        # moments live in two flat buffers (views per parameter), so that a flat gradient bucket can be applied in one launch
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.m_flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v_flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.m, self.v, o = [], [], 0
+        for p in self.params:
+            self.m.append(self.m_flat[o:o + p.numel()].view(p.shape))
+            self.v.append(self.v_flat[o:o + p.numel()].view(p.shape))
+            o += p.numel()
         self.iterations = 0
 
     def step(self, grads):
-        for p, g, m, v in zip(self.params, grads, self.m, self.v):
-            mn = self.max_norm if id(p) in self.maxnorm_ids else 0.0
-            ops.adam_step(p.data, g, m, v, self.iterations, self.lr, self.beta1, self.beta2, self.eps, self.decay,
-                          self.clipvalue, mn)
+        """`grads`: one tensor per parameter.  If they are the views of a flat bucket (`parallel.FlatViews`, what the
+        data-parallel hook returns after the all-reduce) and the parameters are dense, the whole update -- clipvalue +
+        Adam for every tensor -- is ONE kernel launch, followed by the maxnorm constraint of the LSTM kernels."""
+        flat = getattr(grads, "flat", None)
+        if (flat is not None and flat.is_cuda and flat.numel() == self.m_flat.numel() and len(self.params) <= 8
+                and all(p.data.is_contiguous() for p in self.params)):
+            ops.adam_flat([p.data for p in self.params], flat, self.m_flat, self.v_flat, self.iterations, self.lr,
+                          self.beta1, self.beta2, self.eps, self.decay, self.clipvalue)
+            for p in self.params:
+                if id(p) in self.maxnorm_ids:
+                    ops.maxnorm(p.data, self.max_norm)
+        else:
+            for p, g, m, v in zip(self.params, grads, self.m, self.v):
+                mn = self.max_norm if id(p) in self.maxnorm_ids else 0.0
+                ops.adam_step(p.data, g, m, v, self.iterations, self.lr, self.beta1, self.beta2, self.eps, self.decay,
+                              self.clipvalue, mn)
         self.iterations += 1
 
 

@@ -266,6 +266,39 @@ def adam_step(param, grad, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-7, dec
          stream_ptr())
 
 
+def _ptr_table(tensors):
+    """Host arrays (device pointers, element counts) for the multi-tensor entry points."""
+    import ctypes
+    n = len(tensors)
+    ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in tensors])
+    sizes = (ctypes.c_size_t * n)(*[t.numel() for t in tensors])
+    return ptrs, sizes, n
+
+
+def pack(tensors, flat):
+    """flat <- the tensors back to back, one launch (the data-parallel gradient bucket)."""
+    require_cuda(flat, *tensors)
+    ts = [_f32c(t) for t in tensors]
+    ptrs, sizes, n = _ptr_table(ts)
+    call("gr_pack_f32", ptrs, sizes, n, ptr(flat), stream_ptr())
+    return flat
+
+
+def adam_flat(params, flat_grad, flat_m, flat_v, step, lr, beta1=0.9, beta2=0.999, eps=1e-7, decay=0.0, clipvalue=0.0):
+    """clipvalue + Keras Adam on every tensor of `params` in ONE launch; gradients / moments are flat buffers holding the
+    tensors back to back in the same order."""
+    require_cuda(flat_grad, flat_m, flat_v, *params)
+    ptrs, sizes, n = _ptr_table(params)
+    call("gr_adam_flat_f32", ptrs, sizes, n, ptr(flat_grad), ptr(flat_m), ptr(flat_v), float(lr), float(beta1),
+         float(beta2), float(eps), float(decay), float(clipvalue), int(step), stream_ptr())
+
+
+def maxnorm(param, max_norm):
+    require_cuda(param)
+    rows, cols = param.shape[0], param.numel() // param.shape[0]
+    call("gr_maxnorm_f32", ptr(param), rows, cols, float(max_norm), stream_ptr())
+
+
 def dropout_mask(shape, p, seed, offset, device):
     out = torch.empty(shape, dtype=torch.float32, device=device)
     call("gr_dropout_mask_f32", ptr(out), out.numel(), float(p), int(seed), int(offset), stream_ptr())

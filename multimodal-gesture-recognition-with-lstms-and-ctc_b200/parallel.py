@@ -28,6 +28,11 @@ def shard_rows(n_rows, rank, world):
     return (rank * n_rows) // world, ((rank + 1) * n_rows) // world
 
 
+class FlatViews(list):
+    """Per-parameter views of one flat buffer (`.flat`): an optimiser that sees it can update every tensor in one launch."""
+    flat = None
+
+
 class FlatGradBucket:
     """All trainable gradients in one flat fp32 buffer -> a single all-reduce (sum)."""
 
@@ -35,15 +40,20 @@ class FlatGradBucket:
         self.shapes = [tuple(p.shape) for p in params]
         self.sizes = [int(p.numel()) for p in params]
         self.flat = torch.zeros(sum(self.sizes), dtype=torch.float32, device=params[0].device)
-        self.views = []
+        self.views = FlatViews()
+        self.views.flat = self.flat
         o = 0
         for n, s in zip(self.sizes, self.shapes):
             self.views.append(self.flat[o:o + n].view(s))
             o += n
 
     def pack(self, grads):
-        for v, g in zip(self.views, grads):
-            v.copy_(g)
+        if self.flat.is_cuda:
+            from . import ops
+            ops.pack(list(grads), self.flat)          # one launch for all tensors
+        else:
+            for v, g in zip(self.views, grads):       # host-side tests (gloo)
+                v.copy_(g)
         return self.flat
 
     def all_reduce(self):
