@@ -108,8 +108,8 @@ __device__ __forceinline__ void tmem_st_zero_32x8(uint32_t taddr) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z) : "memory");
 }
 
-// NB = batch rows per tile (16, 32, 64, 128); a CTA owns up to two tiles.
-template <int NB>
+// NB = batch rows per tile (16, 32, 64, 128); a CTA owns up to NT tiles (NT * accumulator width <= 256 TMEM columns).
+template <int NB, int NT>
 __global__ void __launch_bounds__(kUThreads, 1)
 lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmG,
                     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmC, LstmTcuParams p) {
@@ -119,6 +119,7 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
   // issue rate (~23 cycles per MMA), not the tensor pipe, bounds the MMA phase: half the instructions, half the time.
   constexpr bool STK = NB <= 32;
   constexpr int DW = STK ? 2 * NB : NB;         // accumulator columns per tile
+  static_assert(NT * DW <= 256 && NT <= 4, "accumulators must fit the 256 TMEM columns beside U");
   constexpr uint32_t kIo = NB * 256;            // P / gates tile: [4 gates][NB rows][16 units] fp32
   constexpr uint32_t kYs = NB * 64;             // y (and c) staging: [NB rows][16 units] fp32
   constexpr uint32_t kSlot = kIo + 2 * kYs;
@@ -128,8 +129,8 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
   uint8_t* slots = ring + (size_t)kURing * kUStage;       // 2 x { io, ystage, cstage }
   uint64_t* full = reinterpret_cast<uint64_t*>(slots + 2 * kSlot);
   uint64_t* empty = full + kURing;
-  uint64_t* tmem_full = empty + kURing;    // [2]  tile's MMAs of this step are complete
-  uint64_t* p_full = tmem_full + 2;        // [2]  P tile of the slot landed (implies: the slot's staging is free)
+  uint64_t* tmem_full = empty + kURing;    // [NT <= 4]  tile's MMAs of this step are complete
+  uint64_t* p_full = tmem_full + 4;        // [2]  P tile of the slot landed (implies: the slot's staging is free)
   uint64_t* stage_ready = p_full + 2;      // [2]  256 epilogue threads staged the slot's outputs
   uint64_t* ld_done = stage_ready + 2;     // 256 epilogue threads hold the tile's accumulator in registers
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(ld_done + 1);
@@ -140,7 +141,7 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
   const int dir = blockIdx.x / (p.UGn * p.NSB);
   const int j0 = ug * kUUnits;
   const int H = p.H, T = p.T;
-  const int ntl = min(2, p.NTg - 2 * sb);               // tiles of this CTA
+  const int ntl = min(NT, p.NTg - NT * sb);             // tiles of this CTA
   const uint32_t stage_bytes = (uint32_t)p.CP * 2u * NB * 128u;
   // When one step's requests of all tiles fit the ring, a stage is only re-used by the SAME tile's next step, whose h
   // exists only after this CTA's epilogue saw the tile's MMAs complete (tmem_full): the stage-release commits (each
@@ -153,7 +154,8 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
     for (int s = 0; s < kURing; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&p_full[s], 1); mbar_init(&stage_ready[s], kUEpi); }
+    for (int s = 0; s < 4; ++s) mbar_init(&tmem_full[s], 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&p_full[s], 1); mbar_init(&stage_ready[s], kUEpi); }
     mbar_init(ld_done, kUEpi);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -206,7 +208,7 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
     uint32_t ph = 0;
     for (int s = 1; s < T; ++s) {
       for (int tau = 0; tau < ntl; ++tau) {
-        const int gt = 2 * sb + tau;
+        const int gt = NT * sb + tau;
         const unsigned* ctr = p.counters + (dir * p.NTg + gt) * 32;
         const unsigned target = (unsigned)s * p.UGn;
         unsigned v;
@@ -306,15 +308,15 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
     // publisher role: thread et < 2*NB converts row et>>1, part et&1 of the staged y tile
     const int prow = et >> 1, ppart = et & 1;
     const size_t R = (size_t)4 * p.Bpad;
-    float c_state[2][X];
+    float c_state[NT][X];
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < NT; ++a)
 #pragma unroll
       for (int mm = 0; mm < X; ++mm) c_state[a][mm] = 0.f;
 
     for (int s = 0; s < T; ++s) {
 #pragma unroll
-      for (int tau = 0; tau < 2; ++tau) {
+      for (int tau = 0; tau < NT; ++tau) {
         if (tau >= ntl) break;
         const int n = s * ntl + tau;
         const int slot = n & 1;
@@ -437,7 +439,7 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
               }
               w[u >> 1] = wv;
             }
-            const size_t rowR = (size_t)(dir * 2 + (s & 1)) * p.Bpad + (size_t)(2 * sb + tau) * NB + prow;
+            const size_t rowR = (size_t)(dir * 2 + (s & 1)) * p.Bpad + (size_t)(NT * sb + tau) * NB + prow;
             uint8_t* dst = p.hx + (((size_t)(j0 >> 6) * 2 + ppart) * R + rowR) * 128 + (size_t)(j0 & 63) * 2;
             *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4*>(dst + 16) = make_uint4(w[4], w[5], w[6], w[7]);
@@ -449,7 +451,7 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
           asm volatile("bar.sync 1, 256;" ::: "memory");
           if (et == 0) {
             TCU_TRACE(7, n);
-            unsigned* ctr = p.counters + (dir * p.NTg + 2 * sb + tau) * 32;
+            unsigned* ctr = p.counters + (dir * p.NTg + NT * sb + tau) * 32;
             asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
           }
           if (et == 0) TCU_TRACE(8, n);
@@ -465,14 +467,14 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
       for (int n = 0; n < min(2, total); ++n) {
         const int s = n / ntl, tau = n - s * ntl;
         mbar_expect_tx(&p_full[n & 1], kIo);
-        tma_load_4d_u(slots + (size_t)(n & 1) * kSlot, &tmG, &p_full[n & 1], j0, (2 * sb + tau) * NB, dir == 0 ? s : T - 1 - s, dir * 4);
+        tma_load_4d_u(slots + (size_t)(n & 1) * kSlot, &tmG, &p_full[n & 1], j0, (NT * sb + tau) * NB, dir == 0 ? s : T - 1 - s, dir * 4);
       }
       int s = 0, tau = 0;
       for (int n = 0; n < total; ++n) {
         const int slot = n & 1;
         uint8_t* io = slots + (size_t)slot * kSlot;
         const int t = dir == 0 ? s : T - 1 - s;
-        const int b0 = (2 * sb + tau) * NB;
+        const int b0 = (NT * sb + tau) * NB;
         mbar_wait(&stage_ready[slot], (uint32_t)(n >> 1) & 1u);
         tma_store_4d_u(&tmY, io + kIo, j0, b0, t, dir);
         if (p.save) {
@@ -486,7 +488,7 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
         for (int a = 0; a < 2; ++a) { if (++tau2 == ntl) { tau2 = 0; ++s2; } }
         if (s2 < T) {
           mbar_expect_tx(&p_full[slot], kIo);
-          tma_load_4d_u(io, &tmG, &p_full[slot], j0, (2 * sb + tau2) * NB, dir == 0 ? s2 : T - 1 - s2, dir * 4);
+          tma_load_4d_u(io, &tmG, &p_full[slot], j0, (NT * sb + tau2) * NB, dir == 0 ? s2 : T - 1 - s2, dir * 4);
         }
         if (++tau == ntl) { tau = 0; ++s; }
       }
@@ -907,20 +909,29 @@ int split_bf16_t_launch(const float* x, int R, int K, int ldx, __nv_bfloat16* hi
                         cudaStream_t s);
 
 struct TcuLayout {
-  int NB, NTg, NSB, Bpad, UGn, Kc, KS, Kp8, CP, NREQ;
+  int NB, NT, NTg, NSB, Bpad, UGn, Kc, KS, Kp8, CP, NREQ;
   size_t off_hx, off_ut_hi, off_ut_lo, off_trace, total, smem;
 };
 static TcuLayout tcu_layout(int B, int H) {
   TcuLayout L;
+  // Two tiles per CTA.  (FOUR 64-row tiles per CTA for B > 128 -- GR_TCU_NT=4 -- were measured SLOWER: 9.7 vs 8.3 us per
+  // step at B=256, H=500.  The single TMA warp and the 4-stage ring serialise the tiles: a 64-row tile needs the whole
+  // ring, so the next tile's first load is issued only when stages drain and its latency is exposed at every tile switch
+  // -- 4 x (3 670 MMA phase + ~700) = 17 500 cycles per step against 14 400 with two 128-row tiles.)
   int nb = 16;
   while (nb < 128 && 2 * nb < B) nb *= 2;
+  int nt = 2;
   if (const char* e = getenv("GR_TCU_NB")) {   // experiments: force the tile width
     const int v = atoi(e);
     if (v == 16 || v == 32 || v == 64 || v == 128) nb = v;
   }
+  if (const char* e = getenv("GR_TCU_NT")) {
+    if (atoi(e) == 4 && B > 128) { nb = 64; nt = 4; }
+  }
   L.NB = nb;
+  L.NT = nt;
   L.NTg = (B + nb - 1) / nb;
-  L.NSB = (L.NTg + 1) / 2;
+  L.NSB = (L.NTg + nt - 1) / nt;
   L.Bpad = L.NTg * nb;
   L.UGn = (H + kUUnits - 1) / kUUnits;
   L.Kc = (H + 63) / 64;
@@ -998,10 +1009,10 @@ int lstm_fwd_tcu_launch(float* gates, const float* U, int B, int T, int H, float
     return GR_OK;
   };
   switch (L.NB) {
-    case 16: return go(lstm_fwd_tcu_kernel<16>);
-    case 32: return go(lstm_fwd_tcu_kernel<32>);
-    case 64: return go(lstm_fwd_tcu_kernel<64>);
-    default: return go(lstm_fwd_tcu_kernel<128>);
+    case 16: return go(lstm_fwd_tcu_kernel<16, 2>);
+    case 32: return go(lstm_fwd_tcu_kernel<32, 2>);
+    case 64: return L.NT == 4 ? go(lstm_fwd_tcu_kernel<64, 4>) : go(lstm_fwd_tcu_kernel<64, 2>);
+    default: return go(lstm_fwd_tcu_kernel<128, 2>);
   }
 }
 
