@@ -296,14 +296,15 @@ int lstm_bwd_tcu_launch(float* gates, const float* cell, const float* dy, const 
 
 // register-resident-U path for narrow layers (lstm_small.cu)
 bool lstm_small_supported(int H);
+bool lstm_small_aligned(const float* gates, const float* cell, const float* dy);   // 16-byte rows for the bulk copies
 int lstm_small_run(bool bwd, float* gates, const float* U, int B, int T, int H, float* y, float* cell,
                    const float* dy, cudaStream_t s);
 
 // GR_LSTM_IMPL = generic | tc | tcu | small forces one implementation (debugging / cross-checks)
-static bool use_small_path(int H) {
+static bool use_small_path(int H, const float* gates, const float* cell, const float* dy) {
   const char* e = getenv("GR_LSTM_IMPL");
   if (e && strcmp(e, "small") != 0) return false;
-  return lstm_small_supported(H);
+  return lstm_small_supported(H) && lstm_small_aligned(gates, cell, dy);
 }
 static bool use_tcu_path(int B, int H) {
   const char* e = getenv("GR_LSTM_IMPL");
@@ -362,7 +363,7 @@ extern "C" int gr_lstm_recurrence_fwd_f32(float* gates, const float* U, int B, i
   size_t need = 0;
   gr_lstm_workspace_bytes(B, H, &need);
   if (workspace_bytes < need) return set_error(GR_EWORKSPACE, "lstm_fwd: workspace too small");
-  if (use_small_path(H))
+  if (use_small_path(H, gates, nullptr, nullptr))
     return lstm_small_run(false, gates, U, B, T, H, y, cell, nullptr, static_cast<cudaStream_t>(stream));
   if (use_tcu_path(B, H))
     return lstm_fwd_tcu_launch(gates, U, B, T, H, y, cell, workspace, static_cast<cudaStream_t>(stream));
@@ -396,7 +397,7 @@ extern "C" int gr_lstm_recurrence_bwd_f32(float* gates, const float* cell, const
   size_t need = 0;
   gr_lstm_workspace_bytes(B, H, &need);
   if (workspace_bytes < need) return set_error(GR_EWORKSPACE, "lstm_bwd: workspace too small");
-  if (use_small_path(H))
+  if (use_small_path(H, gates, cell, dy))
     return lstm_small_run(true, gates, U, B, T, H, nullptr, const_cast<float*>(cell), dy, static_cast<cudaStream_t>(stream));
   if (use_tcu_bwd_path(B, H))
     return lstm_bwd_tcu_launch(gates, cell, dy, U, B, T, H, workspace, static_cast<cudaStream_t>(stream));
