@@ -1,5 +1,5 @@
 timeout 500 python -m pytest tests/test_gpu_ctc.py tests/test_golden.py tests/test_gpu_models.py -q -m gpu --timeout 150 2>&1 | tail -4
-for impl in v4 v2; do
+for impl in v5 v4; do
 GR_CTC_IMPL=$impl timeout 200 python - <<'PY'
 import sys, os; sys.path.insert(0, ".")
 import torch, bench

@@ -59,11 +59,11 @@ def test_fused_logit_mode(cuda, B, T, C, Lmax):
     assert np.abs(grad - ref_g).max() <= GRAD_TOL * np.abs(ref_g).max()
 
 
-@pytest.mark.parametrize("impl", ["v4", "v2"])
+@pytest.mark.parametrize("impl", ["v5", "v4"])
 @pytest.mark.parametrize("Tn", [1, 2, 3, 7, 31, 32, 33, 63, 64, 65, 66, 97, 128, 129])
 def test_chunk_boundaries_and_both_kernels(cuda, monkeypatch, impl, Tn):
     """Sequence lengths around the 32-frame chunk, the meeting row t* = Tn/2 and the 4-row lattice prefetch
-    window; the previous kernel (GR_CTC_IMPL=v2) stays as a cross-check."""
+    window; the round-1 kernel (GR_CTC_IMPL=v4) stays as a cross-check."""
     import mgr_b200 as mgr
     from oracle import ctc_ref
     monkeypatch.setenv("GR_CTC_IMPL", impl)
