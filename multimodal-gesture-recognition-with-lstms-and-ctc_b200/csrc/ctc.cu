@@ -947,6 +947,11 @@ __global__ void __launch_bounds__(64) ctc_loss_grad_kernel_v5(CtcParams p) {
       const int n = ie - ic;
       const int tlo = dir == 0 ? ic : Tn - ie;
       stage_x(Xs, tlo, n);
+      if (ci + 1 < nchunks) {   // the single X buffer of this phase cannot be staged ahead: pull the next chunk into L2 at least
+        const int ic2 = ic + TC, ie2 = min(ic2 + TC, i_end);
+        const float* nx = xb + (size_t)(p.drop + (dir == 0 ? ic2 : Tn - ie2)) * C;
+        if (32 * lane < (ie2 - ic2) * C) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 32 * lane) : "memory");
+      }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
       recentre();
