@@ -731,8 +731,20 @@ extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shif
   int splits = 1;
   const int sms = num_sms();
   if (tiles < sms && p.kb_total >= 8) {
-    splits = (int)min((long long)(2 * sms + tiles - 1) / tiles, (long long)p.kb_total / 4);
-    if (splits < 1) splits = 1;
+    // split K so that the work units (tiles x splits, handed out dynamically) fill whole waves of the SMs: the old
+    // rule (about two units per SM) gave the fusion dW contraction 26 x 12 = 312 units = 2.1 waves, i.e. a third wave
+    // for 16 of them.  Score = wave efficiency x the share of a unit that is main loop (about 8 k-blocks of fill,
+    // drain and atomic epilogue per unit).
+    const int smax = (int)min((long long)(4 * sms + tiles - 1) / tiles, (long long)p.kb_total / 4);
+    double best = -1.0;
+    for (int sp = 1; sp <= smax; ++sp) {
+      const long long units = tiles * sp;
+      const long long waves = (units + sms - 1) / sms;
+      const int kbps = (p.kb_total + sp - 1) / sp;
+      const double score = (double)units / (double)(waves * sms) * ((double)kbps / (double)(kbps + 8));
+      if (score > best + 1e-9) { best = score; splits = sp; }
+    }
+    if (const char* se = getenv("GR_A32_SPLITS")) { const int v = atoi(se); if (v >= 1 && v <= p.kb_total) splits = v; }
   }
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
