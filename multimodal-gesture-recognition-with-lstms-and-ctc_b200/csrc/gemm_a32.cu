@@ -41,6 +41,7 @@ struct A32Params {
   long long* trace;     // debug (GR_A32_TRACE): clock64 stamps [cta][k-block < 64][8]
   int splits, tiles_n, ntiles_total;   // tile t = ((m tile * tiles_n) + (variant group, n tile)) * splits + k split
   int epi_bufs;      // epilogue staging buffers (2, 4 or 6): TMA stores in flight per CTA
+  int bias_vec;      // bias is 16-byte aligned and Nv % 4 == 0: full chunks read it with 128-bit loads
   int epi_stg;       // 1 (GR_A32_EPI=stg): the epilogue warps write the staged chunk themselves (128-byte rows,
                      // coalesced st.global) instead of a TMA tensor store; measured slower (0.83 vs 0.73 ms on the
                      // K = 40 store stream), kept as a cross-check of the TMA path
@@ -575,6 +576,66 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int row = m0 + (int)r;
       const bool add_bias = p.bias != nullptr && z_ == 0;
+      if (p.epi_stg == 2) {
+        // ---- wide coalesced epilogue (GR_A32_EPI=wide; store-stream tiles, one k-block): 128 columns at a time through a
+        // 64 KB swizzled staging tile, then every warp instruction writes 512 contiguous bytes of ONE output row.  Built
+        // to test whether the 128-byte row pieces of the TMA tensor stores were what held the first-layer projections at
+        // 1.7 TB/s of the 7.4 TB/s a plain fill reaches (profiles/r02_store_probe.txt): they were not -- same speed.
+        const int cbase = var * p.Nv + n0;
+        for (int c0 = 0; c0 < BN && n0 + c0 < p.Nv; c0 += 128) {
+          asm volatile("bar.sync 2, 128;" ::: "memory");          // the previous drain has read the staging tile
+#pragma unroll 1
+          for (int q4 = 0; q4 < 4; ++q4) {
+            if (c0 + 32 * q4 >= BN || n0 + c0 + 32 * q4 >= p.Nv) break;
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + c0 + 32 * q4);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int ncol = min(32, p.Nv - (n0 + c0 + 32 * q4));
+            const float* brow = p.bias ? p.bias + cbase + c0 + 32 * q4 : nullptr;
+            const bool bvec = add_bias && p.bias_vec && ncol == 32;
+            float4 bb[8];
+            if (bvec) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) bb[j] = __ldg(reinterpret_cast<const float4*>(brow) + j);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                     __uint_as_float(v[4 * j + 3]));
+              if (bvec) {
+                o.x += bb[j].x; o.y += bb[j].y; o.z += bb[j].z; o.w += bb[j].w;
+              } else if (add_bias) {
+                if (4 * j < ncol) o.x += brow[4 * j];
+                if (4 * j + 1 < ncol) o.y += brow[4 * j + 1];
+                if (4 * j + 2 < ncol) o.z += brow[4 * j + 2];
+                if (4 * j + 3 < ncol) o.w += brow[4 * j + 3];
+              }
+              *reinterpret_cast<float4*>(epi + r * 512u + (uint32_t)q4 * 128u + (((uint32_t)j ^ (r & 7u)) << 4)) = o;
+            }
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          // drain: warp q writes rows 32q .. 32q+31, lane l the 16 bytes of columns 4l .. 4l+3
+          const bool cok = n0 + c0 + 4 * lane < p.Nv && c0 + 4 * lane < BN;
+          const uint32_t q4l = (uint32_t)lane >> 3, jl = (uint32_t)lane & 7u;
+          float* cdst = p.C + (size_t)cbase + c0 + 4 * lane;
+#pragma unroll 4
+          for (int i = 0; i < 32; ++i) {
+            const uint32_t rr = (uint32_t)(q * 32 + i);
+            const float4 o = *reinterpret_cast<const float4*>(epi + rr * 512u + q4l * 128u + ((jl ^ (rr & 7u)) << 4));
+            if (cok && m0 + (int)rr < p.M) *reinterpret_cast<float4*>(cdst + (size_t)(m0 + rr) * p.ldc) = o;
+          }
+        }
+      } else
       for (int vi = 0; vi < p.nvg; ++vi)
       for (int c0 = 0; c0 < BN && n0 + c0 < p.Nv; c0 += 32) {
         const int cbase = (var + vi) * p.Nv + n0;     // first output column of this tile / variant
@@ -593,6 +654,14 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const int ncol = min(32, p.Nv - (n0 + c0));
         const float* brow = p.bias ? p.bias + cbase + c0 : nullptr;
+        // bias of a full 16-byte aligned chunk: eight uniform 128-bit loads (the per-element guarded loads of round 1
+        // cost ~1 ms of the 2.3 ms first-layer projection)
+        const bool bvec = add_bias && p.bias_vec && ncol == 32;
+        float4 bb[8];
+        if (bvec) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bb[j] = __ldg(reinterpret_cast<const float4*>(brow) + j);
+        }
         if (p.use_atomic) {
           if (row < p.M) {
             float* crow = p.C + (size_t)row * p.ldc + cbase + c0;
@@ -616,7 +685,9 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
           for (int j = 0; j < 8; ++j) {
             float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                                    __uint_as_float(v[4 * j + 3]));
-            if (add_bias) {
+            if (bvec) {
+              o.x += bb[j].x; o.y += bb[j].y; o.z += bb[j].z; o.w += bb[j].w;
+            } else if (add_bias) {
               if (4 * j < ncol) o.x += brow[4 * j];
               if (4 * j + 1 < ncol) o.y += brow[4 * j + 1];
               if (4 * j + 2 < ncol) o.z += brow[4 * j + 2];
@@ -703,6 +774,7 @@ extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shif
   A32Params p;
   p.A = A; p.mask = mask; p.bias = bias; p.C = C; p.lda = lda; p.ldc = ldc; p.M = M; p.Nv = Nv; p.K = K;
   p.nvar = nvar; p.rows_per_seq = rows_per_seq; p.row_shift = row_shift; p.transA = transA ? 1 : 0;
+  p.bias_vec = (bias && (Nv % 4) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0) ? 1 : 0;
   const int seqs = ((transA ? K : M) + rows_per_seq - 1) / rows_per_seq;
   p.mask_var_stride = (long long)seqs * (transA ? M : K);
   const int inner = transA ? M : K;
@@ -774,9 +846,15 @@ extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shif
   if (p.kb_total == 1 && !p.use_atomic) {
     const char* eb = getenv("GR_A32_EPI_BUFS");
     stages = 1;
-    p.epi_bufs = eb ? atoi(eb) : 2;   // measured: 2, 4, 6 buffers within noise (the HBM write stream is the limit)
+    p.epi_bufs = eb ? atoi(eb) : 2;   // measured: 2, 4, 6 buffers within noise (the TMA store engine is the limit)
     if (p.epi_bufs != 2 && p.epi_bufs != 4 && p.epi_bufs != 6) p.epi_bufs = 2;
+    // GR_A32_EPI=wide: the wide coalesced epilogue (64 KB staging tile = four 16 KB buffers).  Measured equal to the TMA
+    // stores (1.87 vs 1.74 ms on the speech first-layer projection): the limit of this store stream is not the store
+    // pattern but the instruction latency of the four epilogue warps, one per SM sub-partition (ncu: profiles/r02_*a32_l1*)
+    { const char* es = getenv("GR_A32_EPI");
+      if (p.nvg == 1 && es && es[0] == 'w') { p.epi_stg = 2; p.epi_bufs = 4; } }
     while (p.epi_bufs > 2 && 1024 + stage_bytes + (size_t)p.epi_bufs * kEpiStage + 512 > 227 * 1024) p.epi_bufs -= 2;
+    if (p.epi_stg == 2 && p.epi_bufs < 4) p.epi_stg = 0;   // no room for the 64 KB staging tile: TMA stores
     if (1024 + stage_bytes + (size_t)p.epi_bufs * kEpiStage + 512 > 227 * 1024) return set_error(GR_EUNSUPPORTED, "gemm_a32: tile does not fit shared memory");
   } else
   if (stages < 2) return set_error(GR_EUNSUPPORTED, "gemm_a32: tile does not fit shared memory");

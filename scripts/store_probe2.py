@@ -1,0 +1,27 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from mgr_b200 import ops, layers
+dev = torch.device("cuda:0")
+def timed(fn, n=5):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+BT, T, H = 256000, 1000, 500
+for F in (40, 64, 128):
+    x = torch.randn(BT, F, device=dev); W = torch.randn(F, 8 * H, device=dev) * 0.05; b = torch.zeros(8 * H, device=dev)
+    masks = ((torch.rand(8, BT // T, F, device=dev) > 0.5).float() * 2).contiguous()
+    gates = torch.empty((BT, 8 * H), dtype=torch.float32, device=dev)
+    wt_hi, wt_lo = ops.split_bf16(W, transpose=True)
+    for name, fn in (("masks+bias", lambda: ops.gemm_a32(x, wt_hi, wt_lo, BT, H, F, gates, 8 * H, nvar=8, mask=masks, rows_per_seq=T, bias=b)),
+                     ("masks     ", lambda: ops.gemm_a32(x, wt_hi, wt_lo, BT, H, F, gates, 8 * H, nvar=8, mask=masks, rows_per_seq=T)),
+                     ("bias      ", lambda: ops.gemm_a32(x, wt_hi, wt_lo, BT, 8 * H, F, gates, 8 * H, bias=b)),
+                     ("plain     ", lambda: ops.gemm_a32(x, wt_hi, wt_lo, BT, 8 * H, F, gates, 8 * H))):
+        for env in ({}, {"GR_A32_EPI": "tma"}):
+            for k, v in env.items(): os.environ[k] = v
+            ms = timed(fn)
+            print("F=%d %s %s: %.3f ms = %.0f GB/s written" % (F, name, env, ms, BT * 8 * H * 4 / ms / 1e6), flush=True)
+            for k in env: os.environ.pop(k)
