@@ -577,10 +577,9 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
       const int row = m0 + (int)r;
       const bool add_bias = p.bias != nullptr && z_ == 0;
       if (p.epi_stg == 2) {
-        // ---- wide coalesced epilogue (GR_A32_EPI=wide; store-stream tiles, one k-block): 128 columns at a time through a
-        // 64 KB swizzled staging tile, then every warp instruction writes 512 contiguous bytes of ONE output row.  Built
-        // to test whether the 128-byte row pieces of the TMA tensor stores were what held the first-layer projections at
-        // 1.7 TB/s of the 7.4 TB/s a plain fill reaches (profiles/r02_store_probe.txt): they were not -- same speed.
+        // ---- wide coalesced epilogue (store-stream tiles, one k-block; GR_A32_EPI=tma restores the tensor stores): 128
+        // columns at a time through a 64 KB swizzled staging tile, then every warp instruction writes 512 contiguous
+        // bytes of ONE output row (the 32-column TMA tensor stores write 128-byte row pieces).
         const int cbase = var * p.Nv + n0;
         for (int c0 = 0; c0 < BN && n0 + c0 < p.Nv; c0 += 128) {
           asm volatile("bar.sync 2, 128;" ::: "memory");          // the previous drain has read the staging tile
@@ -624,15 +623,27 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
             }
           }
           asm volatile("bar.sync 2, 128;" ::: "memory");
-          // drain: warp q writes rows 32q .. 32q+31, lane l the 16 bytes of columns 4l .. 4l+3
+          // drain: warp q writes rows 32q .. 32q+31, lane l the 16 bytes of columns 4l .. 4l+3.  Eight rows per
+          // iteration: eight independent LDS.128 (the swizzle term repeats every 8 rows), then eight STG.128 off one
+          // running pointer -- a lone warp per sub-partition is latency-bound, so the loop is kept to ~3 instructions a row
           const bool cok = n0 + c0 + 4 * lane < p.Nv && c0 + 4 * lane < BN;
           const uint32_t q4l = (uint32_t)lane >> 3, jl = (uint32_t)lane & 7u;
-          float* cdst = p.C + (size_t)cbase + c0 + 4 * lane;
-#pragma unroll 4
-          for (int i = 0; i < 32; ++i) {
-            const uint32_t rr = (uint32_t)(q * 32 + i);
-            const float4 o = *reinterpret_cast<const float4*>(epi + rr * 512u + q4l * 128u + ((jl ^ (rr & 7u)) << 4));
-            if (cok && m0 + (int)rr < p.M) *reinterpret_cast<float4*>(cdst + (size_t)(m0 + rr) * p.ldc) = o;
+          const int nrow = min(32, p.M - m0 - q * 32);                // rows of this warp inside the matrix
+          float* cptr = p.C + (size_t)(m0 + q * 32) * p.ldc + cbase + c0 + 4 * lane;
+          const uint8_t* sbase = epi + (uint32_t)(q * 32) * 512u + q4l * 128u;
+          if (cok) {
+#pragma unroll 1
+            for (int i0 = 0; i0 < 32; i0 += 8) {
+              if (i0 >= nrow) break;
+              float4 o[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) o[u] = *reinterpret_cast<const float4*>(sbase + (uint32_t)(i0 + u) * 512u + ((jl ^ (uint32_t)u) << 4));
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                if (i0 + u < nrow) *reinterpret_cast<float4*>(cptr) = o[u];
+                cptr += p.ldc;
+              }
+            }
           }
         }
       } else
@@ -848,11 +859,11 @@ extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shif
     stages = 1;
     p.epi_bufs = eb ? atoi(eb) : 2;   // measured: 2, 4, 6 buffers within noise (the TMA store engine is the limit)
     if (p.epi_bufs != 2 && p.epi_bufs != 4 && p.epi_bufs != 6) p.epi_bufs = 2;
-    // GR_A32_EPI=wide: the wide coalesced epilogue (64 KB staging tile = four 16 KB buffers).  Measured equal to the TMA
-    // stores (1.87 vs 1.74 ms on the speech first-layer projection): the limit of this store stream is not the store
-    // pattern but the instruction latency of the four epilogue warps, one per SM sub-partition (ncu: profiles/r02_*a32_l1*)
+    // store-stream tiles: the wide coalesced epilogue (64 KB staging tile = four 16 KB buffers) unless GR_A32_EPI=tma / stg.
+    // Measured (profiles/r02_store_probe.txt): speech first layer 1.52 ms against 1.73 with the TMA tensor stores, skeletal
+    // 1.10 against 1.13 -- still 2.7 TB/s of the 7.4 TB/s a plain fill reaches: 512-byte pieces of 128 rows, 16 KB apart
     { const char* es = getenv("GR_A32_EPI");
-      if (p.nvg == 1 && es && es[0] == 'w') { p.epi_stg = 2; p.epi_bufs = 4; } }
+      if (p.nvg == 1 && !(es && (es[0] == 't' || es[0] == 's'))) { p.epi_stg = 2; p.epi_bufs = 4; } }
     while (p.epi_bufs > 2 && 1024 + stage_bytes + (size_t)p.epi_bufs * kEpiStage + 512 > 227 * 1024) p.epi_bufs -= 2;
     if (p.epi_stg == 2 && p.epi_bufs < 4) p.epi_stg = 0;   // no room for the 64 KB staging tile: TMA stores
     if (1024 + stage_bytes + (size_t)p.epi_bufs * kEpiStage + 512 > 227 * 1024) return set_error(GR_EUNSUPPORTED, "gemm_a32: tile does not fit shared memory");
