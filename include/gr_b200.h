@@ -151,6 +151,16 @@ int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shift, const fl
                     int rows_per_seq, int nvar, const void* b_hi, const void* b_lo, int ldb,
                     const float* bias, float* C, int ldc, int M, int Nv, int K, int accumulate,
                     void* stream);
+/* Same contraction for masks that are Keras DROPOUT masks: every mask element is either 0 or mask_scale
+ * (= 1/(1-rate), what K.dropout multiplies kept inputs by; speech_lstm_ctc_words.py:61,73 `dropout=`).  The kernel
+ * then splits each loaded fp32 tile once for four variants, keeps/zeroes the packed bf16 words per variant and
+ * applies mask_scale to the accumulator, i.e. it returns mask_scale * ((A o [mask != 0]) B^T) + bias, which equals
+ * the generic result up to fp32 rounding of the products.  A mask element that is neither 0 nor mask_scale is
+ * treated as mask_scale.  mask == NULL: identical to gr_gemm_a32_f32. */
+int gr_gemm_a32_dropout_f32(const float* A, int lda, int transA, int row_shift, const float* mask,
+                            float mask_scale, int rows_per_seq, int nvar, const void* b_hi, const void* b_lo,
+                            int ldb, const float* bias, float* C, int ldc, int M, int Nv, int K,
+                            int accumulate, void* stream);
 /* plain fp32 CUDA-core GEMM with the same contract on unsplit operands (cross-check only). */
 int gr_gemm_simt_f32(const float* A, const float* B, const float* bias, float* C, int M, int N,
                      int K, int lda, int ldb, int ldc, int accumulate, void* stream);

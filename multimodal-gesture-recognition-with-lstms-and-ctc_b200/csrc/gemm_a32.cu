@@ -39,18 +39,25 @@ struct A32Params {
   int lda, ldc, M, Nv, K, BN, nvar, ntile, rows_per_seq, row_shift, transA, aligned4;
   int kb_total, kb_per_split, stages, use_atomic, tmem_cols;
   long long* trace;     // debug (GR_A32_TRACE): clock64 stamps [cta][k-block < 64][8]
+  int trace_off;        // first stage recorded (GR_A32_TRACE_OFF)
   int splits, tiles_n, ntiles_total;   // tile t = ((m tile * tiles_n) + (variant group, n tile)) * splits + k split
+  int korder, mtiles;   // korder (split-K contractions over B*T): t = (k split * mtiles + m tile) * tiles_n + (variant group, n tile),
+                        // so that the CTAs running together share one k range: its rows of A and of dP^T are read from DRAM
+                        // once (k split fastest made every m tile re-read all of dP^T: 13 x 0.8 GB for the fusion dW)
   int epi_bufs;      // epilogue staging buffers (2, 4 or 6): TMA stores in flight per CTA
   int bias_vec;      // bias is 16-byte aligned and Nv % 4 == 0: full chunks read it with 128-bit loads
   int epi_stg;       // 1 (GR_A32_EPI=stg): the epilogue warps write the staged chunk themselves (128-byte rows,
                      // coalesced st.global) instead of a TMA tensor store; measured slower (0.83 vs 0.73 ms on the
                      // K = 40 store stream), kept as a cross-check of the TMA path
   unsigned* sched;   // dynamic tile counter (zeroed per launch): CTAs that get an SM late find less work
+  float out_scale;   // applied to the accumulator before bias / store (binmask: the dropout scale 1/(1-p))
+  int binmask;       // every mask element is 0 or mask_scale (dropout): the producers split each loaded fp32 tile ONCE and
+                     // form the nvg variants by AND-ing the packed bf16 words with the keep bits; scale in the epilogue
   int nvg;   // variants per CTA: 4 when the variant is <= 128 columns wide (one loaded A tile, four masked
              // conversions, four 128-column accumulators), else 1 (two 256-column accumulators, double buffered)
 };
 
-#define A32_TRACE(slot, it) do { if (p.trace && (it) < 64) p.trace[((size_t)blockIdx.x * 64 + (it)) * 16 + (slot)] = clock64(); } while (0)
+#define A32_TRACE(slot, it) do { if (p.trace && (unsigned)((it) - p.trace_off) < 64u) p.trace[((size_t)blockIdx.x * 64 + ((it) - p.trace_off)) * 16 + (slot)] = clock64(); } while (0)
 __device__ __forceinline__ bool a32_elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -95,12 +102,14 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
   uint64_t* fullA = reinterpret_cast<uint64_t*>(epi + (size_t)p.epi_bufs * kEpiStage);
   uint64_t* fullB = fullA + p.stages;
   uint64_t* empty = fullB + p.stages;
-  uint64_t* tmem_full = empty + p.stages;    // [2]
-  uint64_t* tmem_empty = tmem_full + 2;      // [2]
-  uint64_t* sfull = tmem_empty + 2;          // [kSchedDepth] tile id published
+  uint64_t* tmem_full = empty + p.stages;    // [4]: per accumulator buffer (nvg == 1: two) / per variant (nvg == 4)
+  uint64_t* tmem_empty = tmem_full + 4;      // [4]
+  uint64_t* sfull = tmem_empty + 4;          // [kSchedDepth] tile id published
   uint64_t* sempty = sfull + kSchedDepth;    // [kSchedDepth] tile id read by all 14 consumer warps
   int* tile_ring = reinterpret_cast<int*>(sempty + kSchedDepth);
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tile_ring + kSchedDepth);
+  // dropout-mask keep bits of the current / next k-block: [2 slots][4 variants x 2 sequences][4 words]
+  uint32_t* kbits = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(tmem_ptr_s + 1) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // tile decode (identical in every role): t -> (m0, var, n0, k-block range)
@@ -116,9 +125,9 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
   }                                                                            \
   if (tile < 0) break;
 #define A32_TILE_DECODE(t)                                                    \
-  const int z_ = (t) % p.splits;                                              \
-  const int nv_ = ((t) / p.splits) % p.tiles_n;                               \
-  const int m0 = ((t) / p.splits / p.tiles_n) * 128;                          \
+  const int z_ = p.korder ? (t) / (p.tiles_n * p.mtiles) : (t) % p.splits;    \
+  const int nv_ = p.korder ? (t) % p.tiles_n : ((t) / p.splits) % p.tiles_n;  \
+  const int m0 = (p.korder ? ((t) / p.tiles_n) % p.mtiles : (t) / p.splits / p.tiles_n) * 128; \
   const int var = (nv_ / p.ntile) * p.nvg, n0 = (nv_ % p.ntile) * BN;         \
   const int kb_begin = z_ * p.kb_per_split;                                   \
   const int nkb = min(kb_begin + p.kb_per_split, p.kb_total) - kb_begin;
@@ -127,8 +136,8 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBh)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBl)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&fullA[s], 256); mbar_init(&fullB[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&fullA[s], 8); mbar_init(&fullB[s], 1); mbar_init(&empty[s], 1); }   // fullA: one arrival per producer warp
+    for (int b = 0; b < 4; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
     for (int b = 0; b < kSchedDepth; ++b) { mbar_init(&sfull[b], 1); mbar_init(&sempty[b], 14); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -174,13 +183,24 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
       (void)m0; (void)var; (void)n0;
       const int nbuf = p.nvg == 1 ? 2 : 1;
       const int buf = lt % nbuf;
-      mbar_wait(&tmem_empty[buf], (uint32_t)(((lt / nbuf) & 1) ^ 1));   // epilogue drained the accumulator(s)
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // nvg == 1: two 256-column accumulators alternate between tiles.  nvg == 4: the four variants' accumulators are
+      // handed over ONE BY ONE (tmem_full / tmem_empty per variant): variant 0 of the next tile starts as soon as the
+      // epilogue has drained accumulator 0, while it is still draining 1..3 (all four at once stalled the MMA warp
+      // for the whole epilogue, 39 k of 210 k cycles per tile of the fusion projection)
+      if (p.nvg == 1) {
+        mbar_wait(&tmem_empty[buf], (uint32_t)(((lt / nbuf) & 1) ^ 1));   // epilogue drained the accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
       for (int i = 0; i < nkb; ++i)
         for (int vi = 0; vi < p.nvg; ++vi, ++it) {
           const uint32_t acc = tmem_base + (uint32_t)(p.nvg == 1 ? buf * 256 : vi * 128);
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
+          if (p.nvg > 1 && i == 0) {
+            if (lane == 0 && vi == 0) A32_TRACE(10, lt);
+            mbar_wait(&tmem_empty[vi], (uint32_t)((lt & 1) ^ 1));
+            if (lane == 0 && vi == 0) A32_TRACE(11, lt);
+          }
           mbar_wait(&fullB[s], ph);
           if (lane == 0) A32_TRACE(3, it);
           mbar_wait(&fullA[s], ph);
@@ -200,7 +220,10 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
               umma_bf16(acc, dAl + adv, dBh + adv, idesc, 1u);
             }
             umma_commit(&empty[s]);
-            if (i == nkb - 1 && vi == p.nvg - 1) umma_commit(&tmem_full[buf]);
+            if (i == nkb - 1) {
+              if (p.nvg > 1) umma_commit(&tmem_full[vi]);
+              else umma_commit(&tmem_full[buf]);
+            }
           }
           __syncwarp();
           if (lane == 0) A32_TRACE(5, it);
@@ -210,6 +233,8 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
     // =============== A producers: 8 warps, 256 threads ===============
     const int t = threadIdx.x - 64;  // 0..255
     int it = 0;
+    int gblk = 0;   // k-blocks handled so far (all tiles): slot parity of the keep-bit ring
+    (void)gblk; (void)kbits;
     for (int tn = 0;; ++tn) {
     A32_NEXT_TILE(tn, tile)
     A32_TILE_DECODE(tile)
@@ -247,7 +272,79 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
           mB = kv ? __ldg(reinterpret_cast<const float4*>(mpB + koff)) : zero4;
         }
       };
-      if (p.nvg > 1) {
+      if (p.nvg > 1 && p.binmask) {
+        // ---- four variants per CTA, masks in {0, s}: the fp32 tile of k-block i is loaded and split ONCE; variant vi
+        //      stores the packed hi / lo words AND-ed with its keep bits (s is applied by the epilogue).  The fp32
+        //      registers are free right after the split, so the loads of k-block i+1 have four stages to land.
+        //      Keep bits: no per-stage global mask loads (their latency was exposed every stage: 2 200 cycles per
+        //      stage with 600 of work) -- producer warp w owns row (variant w/2, sequence w%2) of the mask, loads the 64
+        //      floats of the NEXT k-block one block ahead, ballots them into two words of a 2-slot shared ring; one
+        //      named barrier per k-block, then every thread picks its 8 nibbles.
+        auto ldx = [&](int i) {
+          const int koff = (kb_begin + i) * kBK;
+          const bool kv = koff + kq * 4 < p.K;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xa[j] = (kv && rok[j]) ? __ldg(reinterpret_cast<const float4*>(ap[j] + koff)) : zero4;
+        };
+        const int bw = t >> 5, bl = t & 31;
+        const float* mrow = mv + (long long)(bw >> 1) * p.mask_var_stride + (size_t)((bw & 1) ? min(seqA + 1, nseq - 1) : seqA) * p.K;
+        float f0 = 0.f, f1 = 0.f;
+        auto bld = [&](int i) {
+          const int k = (kb_begin + i) * kBK + bl;
+          f0 = (i < nkb && k < p.K) ? __ldg(mrow + k) : 0.f;
+          f1 = (i < nkb && k + 32 < p.K) ? __ldg(mrow + k + 32) : 0.f;
+        };
+        if (nkb > 0) { ldx(0); bld(0); }
+        for (int i = 0; i < nkb; ++i, ++gblk) {
+          // publish the keep bits of block i (loaded one block ago), prefetch those of block i+1
+          {
+            const uint32_t b0 = __ballot_sync(0xffffffffu, f0 != 0.f), b1 = __ballot_sync(0xffffffffu, f1 != 0.f);
+            if (bl == 0) *reinterpret_cast<uint2*>(&kbits[((gblk & 1) * 8 + bw) * 4]) = make_uint2(b0, b1);
+          }
+          bld(i + 1);
+          if (t == 0) A32_TRACE(7, it);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (t == 0) A32_TRACE(8, it);
+          uint32_t nib = 0;     // nibble (vi*2 + sel): keep bits of this thread's four k
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            nib |= ((kbits[((gblk & 1) * 8 + r) * 4 + (kq >> 3)] >> ((kq & 7) * 4)) & 0xfu) << (4 * r);
+          uint2 hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            split_pair(xa[j].x, xa[j].y, hi[j].x, lo[j].x);
+            split_pair(xa[j].z, xa[j].w, hi[j].y, lo[j].y);
+          }
+          if (t == 0 && p.trace) { if (hi[7].y == 0x12345678u) p.trace[0] = 1; A32_TRACE(9, it); }
+          if (i + 1 < nkb) ldx(i + 1);
+          if (t == 0) A32_TRACE(12, it);
+#pragma unroll
+          for (int vi = 0; vi < 4; ++vi, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (it / p.stages) & 1;
+            uint8_t* Ah = smem + (size_t)s * stage_bytes + off0;
+            uint8_t* Al = Ah + a_bytes;
+            const uint32_t nA = nib >> (8 * vi), nB = nib >> (8 * vi + 4);
+            const uint2 zA = make_uint2(((nA & 1u) ? 0x0000ffffu : 0u) | ((nA & 2u) ? 0xffff0000u : 0u),
+                                        ((nA & 4u) ? 0x0000ffffu : 0u) | ((nA & 8u) ? 0xffff0000u : 0u));
+            const uint2 zB = make_uint2(((nB & 1u) ? 0x0000ffffu : 0u) | ((nB & 2u) ? 0xffff0000u : 0u),
+                                        ((nB & 4u) ? 0x0000ffffu : 0u) | ((nB & 8u) ? 0xffff0000u : 0u));
+            if (t == 0) A32_TRACE(0, it);
+            mbar_wait(&empty[s], ph ^ 1);
+            if (t == 0) A32_TRACE(1, it);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint2 z = selB[j] ? zB : zA;
+              *reinterpret_cast<uint2*>(Ah + j * 2048) = make_uint2(hi[j].x & z.x, hi[j].y & z.y);
+              *reinterpret_cast<uint2*>(Al + j * 2048) = make_uint2(lo[j].x & z.x, lo[j].y & z.y);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
+            if (t == 0) A32_TRACE(2, it);
+          }
+        }
+      } else if (p.nvg > 1) {
         // ---- several variants per CTA: the fp32 tile of k-block i is loaded ONCE and converted nvg
         //      times, each time under the dropout mask of one variant (masks prefetched one ahead)
         auto ldmask = [&](int q, float4& mA, float4& mB) {
@@ -290,7 +387,8 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
           }
           if (++vi == p.nvg) { vi = 0; ++i; if (i < nkb) ldx(i); }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
           if (t == 0) A32_TRACE(2, it);
           mAa = mAn; mBa = mBn;
         }
@@ -324,7 +422,8 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (t == 0) A32_TRACE(12, it);
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
         if (t == 0) A32_TRACE(2, it);
       }
       }
@@ -368,7 +467,80 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
         }
       };
       ma[0] = ma[1] = one4;
-      if (p.nvg > 1) {
+      if (p.nvg > 1 && p.binmask) {
+        // ---- four variants per CTA, masks in {0, s} (see MODE 1): one load and ONE split of the k-block; a variant's
+        //      row g is the packed words or zeros (one AND per word; the per-k select only in the rare chunk that
+        //      straddles two sequences).  Keep bits through the shared ring: warp w owns (variant w/2, sequence
+        //      seq0 + w%2) and ballots the mask of the tile's 128 rows into four words.
+        const int bw = t >> 5, bl = t & 31;
+        float f[4] = {0.f, 0.f, 0.f, 0.f};
+        auto bld = [&](int i) {
+          const int seq0 = ((kb_begin + min(i, nkb - 1)) * kBK) / T_;
+          const float* mrow = mv + (long long)(bw >> 1) * p.mask_var_stride + (size_t)min(seq0 + (bw & 1), nseq - 1) * p.M + m0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) f[u] = (i < nkb && m0 + 32 * u + bl < p.M) ? __ldg(mrow + 32 * u + bl) : 0.f;
+        };
+        float4 dummy[2];
+        if (nkb > 0) { ld(0, xa, dummy, selA_mask); bld(0); }
+        for (int i = 0; i < nkb; ++i, ++gblk) {
+          {
+            uint32_t b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) b[u] = __ballot_sync(0xffffffffu, f[u] != 0.f);
+            if (bl == 0) *reinterpret_cast<uint4*>(&kbits[((gblk & 1) * 8 + bw) * 4]) = make_uint4(b[0], b[1], b[2], b[3]);
+          }
+          bld(i + 1);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          uint32_t nib = 0;     // nibble (vi*2 + sel): keep bits of this thread's four tile rows
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            nib |= ((kbits[((gblk & 1) * 8 + r) * 4 + (rloc >> 5)] >> (rloc & 31)) & 0xfu) << (4 * r);
+          uint32_t hh[4][4], ll[4][4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int kk = 0; kk < 8; kk += 2) {
+              const float4 v0 = xa[kk], v1 = xa[kk + 1];
+              const float e0 = g == 0 ? v0.x : g == 1 ? v0.y : g == 2 ? v0.z : v0.w;
+              const float e1 = g == 0 ? v1.x : g == 1 ? v1.y : g == 2 ? v1.z : v1.w;
+              split_pair(e0, e1, hh[g][kk >> 1], ll[g][kk >> 1]);
+            }
+          const int sel = selA_mask;
+          if (i + 1 < nkb) ld(i + 1, xa, dummy, selA_mask);
+#pragma unroll
+          for (int vi = 0; vi < 4; ++vi, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (it / p.stages) & 1;
+            uint8_t* Ah = smem + (size_t)s * stage_bytes;
+            uint8_t* Al = Ah + a_bytes;
+            const uint32_t kb = nib >> (8 * vi);
+            if (t == 0) A32_TRACE(0, it);
+            mbar_wait(&empty[s], ph ^ 1);
+            if (t == 0) A32_TRACE(1, it);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const bool k0 = (kb >> g) & 1u, k1 = (kb >> (4 + g)) & 1u;
+              uint32_t z[4];
+              if (sel == 0) {
+                z[0] = z[1] = z[2] = z[3] = k0 ? 0xffffffffu : 0u;
+              } else {
+#pragma unroll
+                for (int w = 0; w < 4; ++w)
+                  z[w] = ((((sel >> (2 * w)) & 1) ? k1 : k0) ? 0x0000ffffu : 0u) |
+                         ((((sel >> (2 * w + 1)) & 1) ? k1 : k0) ? 0xffff0000u : 0u);
+              }
+              const uint32_t r = (uint32_t)(rloc + g);
+              const uint32_t off = r * 128u + (((uint32_t)kc ^ (r & 7u)) << 4);
+              *reinterpret_cast<uint4*>(Ah + off) = make_uint4(hh[g][0] & z[0], hh[g][1] & z[1], hh[g][2] & z[2], hh[g][3] & z[3]);
+              *reinterpret_cast<uint4*>(Al + off) = make_uint4(ll[g][0] & z[0], ll[g][1] & z[1], ll[g][2] & z[2], ll[g][3] & z[3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
+            if (t == 0) A32_TRACE(2, it);
+          }
+        }
+      } else if (p.nvg > 1) {
         // ---- several variants per CTA (see MODE 1): one load of the k-block, nvg masked conversions
         auto ldmask = [&](int q, float4* mk) {
           const int i = q / p.nvg, vi = q - i * p.nvg;
@@ -415,7 +587,8 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
           }
           if (++vi == p.nvg) { vi = 0; ++i; if (i < nkb) ld(i, xa, dummy, selA_mask); }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
           if (t == 0) A32_TRACE(2, it);
           ma[0] = mn[0]; ma[1] = mn[1];
         }
@@ -452,7 +625,8 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
         }
         if (i + 1 < nkb) ld(i + 1, xa, ma, selA_mask);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
         if (t == 0) A32_TRACE(2, it);
       }
       }
@@ -554,7 +728,8 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
     }
     }
     }  // tile loop (producers)
@@ -571,9 +746,11 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
       const int nbuf = p.nvg == 1 ? 2 : 1;
       const int buf = lt % nbuf;
       if (et == 0) A32_TRACE(13, lt);
-      mbar_wait(&tmem_full[buf], (uint32_t)((lt / nbuf) & 1));
+      if (p.nvg == 1) {
+        mbar_wait(&tmem_full[buf], (uint32_t)((lt / nbuf) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
       if (et == 0) A32_TRACE(14, lt);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int row = m0 + (int)r;
       const bool add_bias = p.bias != nullptr && z_ == 0;
       if (p.epi_stg == 2) {
@@ -647,7 +824,11 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
           }
         }
       } else
-      for (int vi = 0; vi < p.nvg; ++vi)
+      for (int vi = 0; vi < p.nvg; ++vi) {
+      if (p.nvg > 1) {
+        mbar_wait(&tmem_full[vi], (uint32_t)(lt & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
       for (int c0 = 0; c0 < BN && n0 + c0 < p.Nv; c0 += 32) {
         const int cbase = (var + vi) * p.Nv + n0;     // first output column of this tile / variant
         uint32_t v[32];
@@ -672,6 +853,10 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
         if (bvec) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) bb[j] = __ldg(reinterpret_cast<const float4*>(brow) + j);
+        }
+        if (p.binmask) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) * p.out_scale);
         }
         if (p.use_atomic) {
           if (row < p.M) {
@@ -730,10 +915,17 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
           ++cc;
         }
       }
+      if (p.nvg > 1) {   // accumulator vi is free for the next tile
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[vi])) : "memory");
+      }
+      }
       if (et == 0) A32_TRACE(15, lt);
-      // this accumulator may be overwritten by the MMA warp (tile lt + 2)
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+      if (p.nvg == 1) {
+        // this accumulator may be overwritten by the MMA warp (tile lt + 2)
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[buf])) : "memory");
+      }
     }
     if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else {
@@ -769,10 +961,32 @@ extern "C" int gr_debug_a32_trace(long long* host_out, size_t n) {
   return cudaMemcpy(host_out, g_a32_trace, n * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
 }
 
+static int gemm_a32_launch(const float* A, int lda, int transA, int row_shift, const float* mask, float mask_scale,
+                           int rows_per_seq, int nvar, const void* b_hi, const void* b_lo, int ldb,
+                           const float* bias, float* C, int ldc, int M, int Nv, int K, int accumulate,
+                           void* stream);
+
 extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shift, const float* mask,
                                int rows_per_seq, int nvar, const void* b_hi, const void* b_lo, int ldb,
                                const float* bias, float* C, int ldc, int M, int Nv, int K, int accumulate,
                                void* stream) {
+  return gemm_a32_launch(A, lda, transA, row_shift, mask, 0.f, rows_per_seq, nvar, b_hi, b_lo, ldb, bias, C, ldc, M, Nv, K,
+                         accumulate, stream);
+}
+
+extern "C" int gr_gemm_a32_dropout_f32(const float* A, int lda, int transA, int row_shift, const float* mask,
+                                       float mask_scale, int rows_per_seq, int nvar, const void* b_hi, const void* b_lo,
+                                       int ldb, const float* bias, float* C, int ldc, int M, int Nv, int K,
+                                       int accumulate, void* stream) {
+  if (mask && !(mask_scale > 0.f)) return gr::set_error(GR_EINVAL, "gemm_a32_dropout: mask_scale must be > 0");
+  return gemm_a32_launch(A, lda, transA, row_shift, mask, mask ? mask_scale : 0.f, rows_per_seq, nvar, b_hi, b_lo, ldb, bias,
+                         C, ldc, M, Nv, K, accumulate, stream);
+}
+
+static int gemm_a32_launch(const float* A, int lda, int transA, int row_shift, const float* mask, float mask_scale,
+                           int rows_per_seq, int nvar, const void* b_hi, const void* b_lo, int ldb,
+                           const float* bias, float* C, int ldc, int M, int Nv, int K, int accumulate,
+                           void* stream) {
   using namespace gr;
   if (!A || !b_hi || !b_lo || !C) return set_error(GR_EINVAL, "gemm_a32: null pointer");
   if (M <= 0 || Nv <= 0 || K <= 0 || nvar <= 0 || rows_per_seq <= 0 || ldc < nvar * Nv)
@@ -809,7 +1023,13 @@ extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shif
   // prefetch already hides the loads, and both are near the shared-memory bandwidth bound); GR_A32_NVG=4
   // forces it there too, GR_A32_NVG=1 disables it
   const bool nvg_ok = mode != 0 && mask && (nvar % 4) == 0 && p.ntile == 1 && p.BN <= 128;
-  p.nvg = nvg_ok && ((mode == 2 && !(nvg_env && nvg_env[0] == '1')) || (nvg_env && nvg_env[0] == '4')) ? 4 : 1;
+  // masks known to be {0, mask_scale} (gr_gemm_a32_dropout_f32): one split per loaded tile serves all four variants, which
+  // makes the shared tile pay for the row-major operand too; GR_A32_BINMASK=0 falls back to the multiply path
+  const char* bm_env = getenv("GR_A32_BINMASK");
+  const bool bin_ok = nvg_ok && mask_scale > 0.f && !(bm_env && bm_env[0] == '0');
+  p.nvg = nvg_ok && (((mode == 2 || bin_ok) && !(nvg_env && nvg_env[0] == '1')) || (nvg_env && nvg_env[0] == '4')) ? 4 : 1;
+  p.binmask = (bin_ok && p.nvg == 4) ? 1 : 0;
+  p.out_scale = p.binmask ? mask_scale : 1.f;
   const long long tiles = (long long)mt * p.ntile * (nvar / p.nvg);
   int splits = 1;
   const int sms = num_sms();
@@ -839,12 +1059,16 @@ extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shif
   p.sched = g_a32_sched + (__atomic_fetch_add(&g_a32_sched_next, 1u, __ATOMIC_RELAXED) % kSchedSlots);
   GR_CUDA(cudaMemsetAsync(p.sched, 0, sizeof(unsigned), s));
   p.trace = nullptr;
+  p.trace_off = 0;
+  if (const char* to = getenv("GR_A32_TRACE_OFF")) p.trace_off = atoi(to);
   if (getenv("GR_A32_TRACE")) {
     if (!g_a32_trace) GR_CUDA(cudaMalloc(&g_a32_trace, (size_t)160 * 64 * 16 * 8));
     GR_CUDA(cudaMemsetAsync(g_a32_trace, 0, (size_t)160 * 64 * 16 * 8, s));
     p.trace = g_a32_trace;
   }
   p.splits = splits;
+  p.mtiles = mt;
+  { const char* ko = getenv("GR_A32_KORDER"); p.korder = (splits > 1 && !(ko && ko[0] == '0')) ? 1 : 0; }
   p.tiles_n = p.ntile * (nvar / p.nvg);
   p.ntiles_total = (int)(tiles * splits);
   const size_t stage_bytes = 2 * ((size_t)128 * kBK * 2 + (size_t)p.BN * kBK * 2);
@@ -871,7 +1095,7 @@ extern "C" int gr_gemm_a32_f32(const float* A, int lda, int transA, int row_shif
   if (stages < 2) return set_error(GR_EUNSUPPORTED, "gemm_a32: tile does not fit shared memory");
   p.stages = stages;
   p.tmem_cols = 512;   // two accumulators of <= 256 columns
-  const size_t smem = 1024 + stages * stage_bytes + (size_t)p.epi_bufs * kEpiStage + (3 * stages + 4 + 2 * kSchedDepth) * 8 + kSchedDepth * 4 + 16;
+  const size_t smem = 1024 + stages * stage_bytes + (size_t)p.epi_bufs * kEpiStage + (3 * stages + 8 + 2 * kSchedDepth) * 8 + kSchedDepth * 4 + 16 + 16 + 256;
   CUtensorMap tBh, tBl, tC;
   int rc;
   if ((rc = make_map(&tBh, b_hi, (uint64_t)nvar * Nv, ldb, ldb, p.BN)) != GR_OK) return rc;

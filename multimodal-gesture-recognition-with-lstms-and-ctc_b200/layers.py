@@ -20,9 +20,10 @@ from . import ops
 GEMM_PASSES = 3  # bf16x3 (fp32-faithful) tensor-core projections; 1 = plain bf16
 
 
-def _project(x2, W, b, masks, B, T, H, passes=3):
+def _project(x2, W, b, masks, B, T, H, passes=3, mask_scale=0.0):
     """Hoisted input projection P = (X o mask_g) W_g + b -> (B*T, 8H) on tcgen05.  X stays fp32 in
-    HBM: masking and the bf16 hi/lo split are fused into the GEMM's producer warps."""
+    HBM: masking and the bf16 hi/lo split are fused into the GEMM's producer warps.
+    `mask_scale` > 0: the masks are dropout masks with values in {0, mask_scale}."""
     BT, F = x2.shape
     gates = torch.empty((BT, 8 * H), dtype=torch.float32, device=x2.device)
     wt_hi, wt_lo = ops.split_bf16(W, transpose=True)  # (8H, pad8(F)): B operand, K-major
@@ -37,13 +38,14 @@ def _project(x2, W, b, masks, B, T, H, passes=3):
     if masks is None:
         ops.gemm_a32(x2, wt_hi, wt_lo, BT, 8 * H, F, gates, 8 * H, bias=b)
     else:
-        ops.gemm_a32(x2, wt_hi, wt_lo, BT, H, F, gates, 8 * H, nvar=8, mask=masks, rows_per_seq=T, bias=b)
+        ops.gemm_a32(x2, wt_hi, wt_lo, BT, H, F, gates, 8 * H, nvar=8, mask=masks, rows_per_seq=T, bias=b,
+                     mask_scale=mask_scale)
     return gates
 
 
 class _BlstmFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, W, U, b, masks, passes):
+    def forward(ctx, x, W, U, b, masks, passes, mask_scale=0.0):
         B, T, F = x.shape
         H = U.shape[1]
         # raw pointers cross the C ABI: every operand must be dense row-major
@@ -51,8 +53,9 @@ class _BlstmFn(torch.autograd.Function):
         masks = None if masks is None else masks.contiguous()
         x2 = x.reshape(B * T, F)
         need_grad = any(ctx.needs_input_grad[:4])
-        gates = _project(x2, W, b, masks, B, T, H)
+        gates = _project(x2, W, b, masks, B, T, H, mask_scale=mask_scale)
         y, cell = ops.lstm_recurrence_fwd(gates, U, B, T, H, keep_cell=need_grad)
+        ctx.mask_scale = mask_scale
         if need_grad:
             ctx.save_for_backward(x, W, U, masks, gates, cell, y)
         return y
@@ -76,7 +79,8 @@ class _BlstmFn(torch.autograd.Function):
             if masks is None:
                 ops.gemm_a32(x2, dpt_hi, dpt_lo, F, 8 * H, BT, dW, 8 * H, transA=True, rows_per_seq=T)
             else:
-                ops.gemm_a32(x2, dpt_hi, dpt_lo, F, H, BT, dW, 8 * H, nvar=8, mask=masks, rows_per_seq=T, transA=True)
+                ops.gemm_a32(x2, dpt_hi, dpt_lo, F, H, BT, dW, 8 * H, nvar=8, mask=masks, rows_per_seq=T, transA=True,
+                             mask_scale=ctx.mask_scale)
         if ctx.needs_input_grad[2]:
             # dU_d = H_prev^T dP_d : A = y shifted by one step inside each sequence
             dU = torch.empty((2, H, 4 * H), dtype=torch.float32, device=x.device)
@@ -97,13 +101,15 @@ class _BlstmFn(torch.autograd.Function):
                     ops.gemm_a32(dP, w_hi, w_lo, BT, F, H, tmp, F, a_col_offset=n0)
                     ops.mask_mul_acc(dx2, tmp, masks[dg], T, accumulate=dg > 0)
             dx = dx2.reshape(B, T, F)
-        return dx, dW, dU, db, None, None
+        return dx, dW, dU, db, None, None, None
 
 
-def blstm(x, W, U, b, masks=None, passes=None):
+def blstm(x, W, U, b, masks=None, passes=None, mask_scale=0.0):
     """Functional form.  W (F,8H) = [fwd kernel | bwd kernel]; U (2,H,4H); b (8H);
-    masks None or (8, B, F): input-dropout masks for (dir, gate) = (0,i),(0,f),(0,c),(0,o),(1,i).."""
-    return _BlstmFn.apply(x, W, U, b, masks, GEMM_PASSES if passes is None else passes)
+    masks None or (8, B, F): input-dropout masks for (dir, gate) = (0,i),(0,f),(0,c),(0,o),(1,i)..;
+    mask_scale > 0 declares them Keras dropout masks, every element 0 or mask_scale = 1/(1-rate)
+    (lets the projection kernels share one bf16 split between the four gates of a direction)."""
+    return _BlstmFn.apply(x, W, U, b, masks, GEMM_PASSES if passes is None else passes, float(mask_scale))
 
 
 class _DirView:
@@ -170,8 +176,11 @@ class BidirectionalLSTM(nn.Module):
             return None
         return ops.dropout_mask((8, B, self.input_dim), self.dropout, seed, offset, self.kernel.device)
 
-    def forward(self, x, masks=None):
-        return blstm(x, self.kernel, self.recurrent_kernel, self.bias, masks)
+    def forward(self, x, masks=None, dropout_masks=False):
+        """`dropout_masks=True`: `masks` came from `make_masks` / `ops.dropout_mask` with this layer's rate, i.e. every
+        element is 0 or 1/(1-rate) (injected masks with other values must leave it False)."""
+        scale = 1.0 / (1.0 - self.dropout) if (dropout_masks and masks is not None and 0.0 < self.dropout < 1.0) else 0.0
+        return blstm(x, self.kernel, self.recurrent_kernel, self.bias, masks, mask_scale=scale)
 
 
 class _DenseSoftmaxFn(torch.autograd.Function):

@@ -46,6 +46,7 @@ class UnimodalNet(nn.Module):
             reg["m2"] = ops.dropout_mask((8, B, 2 * self.units), self.p2, seed + 2, off, device)
         if self.pd > 0:
             reg["drop"] = ops.dropout_mask((B, T, 2 * self.units), self.pd, seed + 3, off, device)
+        reg["dropout_masks"] = True    # m1 / m2 hold only 0 and 1/(1-p): see BidirectionalLSTM.forward
         return reg
 
     def tower(self, x, reg=None, merged=None, col0=0):
@@ -54,8 +55,9 @@ class UnimodalNet(nn.Module):
         reg = reg or {}
         if reg.get("noise") is not None:
             x = ops.add(x, reg["noise"])
-        y1 = self.blstm_1(x, reg.get("m1"))
-        y2 = self.blstm_2(y1, reg.get("m2"))
+        dm = bool(reg.get("dropout_masks", False))
+        y1 = self.blstm_1(x, reg.get("m1"), dm)
+        y2 = self.blstm_2(y1, reg.get("m2"), dm)
         if merged is not None:
             return ops.add_into(y1, y2, merged, col0)
         return _add(y1, y2)
@@ -124,7 +126,8 @@ class FusionNet(nn.Module):
         sk.pop("drop", None)
         sk.pop("noise", None)  # GaussianNoise(0.0) on the skeletal branch (multimodal.py:105)
         reg["sp"], reg["sk"] = sp, sk
-        reg["m3"] = ops.dropout_mask((8, B, self.blstm_3.input_dim), 0.5, seed + 30, off, device)
+        reg["m3"] = ops.dropout_mask((8, B, self.blstm_3.input_dim), self.blstm_3.dropout, seed + 30, off, device)
+        reg["dropout_masks"] = True
         reg["drop"] = ops.dropout_mask((B, T, 2 * self.units), 0.5, seed + 31, off, device)
         return reg
 
@@ -165,12 +168,16 @@ class FusionNet(nn.Module):
                 h = B // 2
                 sp = reg.get("sp") or {}
 
+                def _cut(d, lo, hi):
+                    return {k: (v if not torch.is_tensor(v) else v[lo:hi] if k == "noise" else v[:, lo:hi].contiguous())
+                            for k, v in d.items()}
+
                 def half(lo, hi):
-                    return {k: (v[lo:hi] if k == "noise" else v[:, lo:hi].contiguous()) for k, v in sp.items()}
+                    return _cut(sp, lo, hi)
                 sk = reg.get("sk") or {}
 
                 def half_sk(lo, hi):
-                    return {k: (v[lo:hi] if k == "noise" else v[:, lo:hi].contiguous()) for k, v in sk.items()}
+                    return _cut(sk, lo, hi)
                 if split == "2":   # the skeletal tower in halves as well (38 CTAs each): 51.3 -> 49.2 ms/step
                     work = [(sa, lambda: self.speech.tower(xa[:h], half(0, h), merged[:h], 0)),
                             (sb, lambda: self.skeletal.tower(xs[:h], half_sk(0, h), merged[:h], fa)),
@@ -208,7 +215,7 @@ class FusionNet(nn.Module):
     def forward(self, xa, xs, reg=None):
         reg = reg or {}
         m = self.merged(xa, xs, reg)
-        y3 = self.blstm_3(m, reg.get("m3"))
+        y3 = self.blstm_3(m, reg.get("m3"), bool(reg.get("dropout_masks", False)))
         return self.dense(y3, reg.get("drop"))
 
     # ------------------------------------------------------------------ explicit training step
@@ -224,7 +231,7 @@ class FusionNet(nn.Module):
         lab_i, il, ll = _prep_lengths(labels, input_length, label_length, xa.device)
         m = self.join_towers(towers) if towers is not None else self.merged(xa, xs, reg)
         l3 = self.blstm_3
-        y3 = l3(m, reg.get("m3"))                      # autograd node (kernel-backed)
+        y3 = l3(m, reg.get("m3"), bool(reg.get("dropout_masks", False)))   # autograd node (kernel-backed)
         H2 = 2 * self.units
         y3_2d = y3.detach().reshape(B * T, H2)
         dm = reg.get("drop")

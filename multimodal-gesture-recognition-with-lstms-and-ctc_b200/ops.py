@@ -129,15 +129,21 @@ def gemm_nt(a_hi, a_lo, b_hi, b_lo, M, N, K, out=None, ldc=None, bias=None, accu
 
 
 def gemm_a32(A2d, b_hi, b_lo, M, Nv, K, out, ldc, nvar=1, mask=None, rows_per_seq=1, transA=False, row_shift=0,
-             bias=None, accumulate=False, a_col_offset=0, out_col_offset=0):
+             bias=None, accumulate=False, a_col_offset=0, out_col_offset=0, mask_scale=0.0):
     """Fused-prologue projection GEMM (gr_gemm_a32_f32): A stays fp32 in HBM; mask / hi-lo split /
-    transpose / time shift happen in the kernel's producer warps.  A2d: (rows, lda) fp32."""
+    transpose / time shift happen in the kernel's producer warps.  A2d: (rows, lda) fp32.
+    `mask_scale` > 0 declares `mask` a dropout mask with values in {0, mask_scale} (gr_gemm_a32_dropout_f32)."""
     import ctypes
     require_cuda(A2d, b_hi, b_lo, out, bias, mask)
     assert A2d.dim() == 2 and A2d.stride(1) == 1
     aptr = ctypes.c_void_p(A2d.data_ptr() + 4 * a_col_offset)
     cptr = ctypes.c_void_p(out.data_ptr() + 4 * out_col_offset)
     _lib.note_work(2.0 * M * Nv * nvar * K)
+    if mask is not None and mask_scale > 0.0:
+        call("gr_gemm_a32_dropout_f32", aptr, A2d.stride(0), int(bool(transA)), int(row_shift), ptr(mask),
+             float(mask_scale), int(rows_per_seq), int(nvar), ptr(b_hi), ptr(b_lo), b_hi.stride(0), ptr(bias), cptr,
+             int(ldc), int(M), int(Nv), int(K), int(bool(accumulate)), stream_ptr())
+        return out
     call("gr_gemm_a32_f32", aptr, A2d.stride(0), int(bool(transA)), int(row_shift), ptr(mask), int(rows_per_seq),
          int(nvar), ptr(b_hi), ptr(b_lo), b_hi.stride(0), ptr(bias), cptr, int(ldc), int(M), int(Nv), int(K),
          int(bool(accumulate)), stream_ptr())

@@ -43,9 +43,10 @@ def run(lo, hi, hook_factory):
         out = {"sp": {}, "sk": {}}
         for t in ("sp", "sk"):
             for k, v in reg[t].items():
-                out[t][k] = cut(v, 0 if k in ("noise", "drop") else 1)
+                out[t][k] = cut(v, 0 if k in ("noise", "drop") else 1) if torch.is_tensor(v) else v
         out["m3"] = cut(reg["m3"], 1)
         out["drop"] = cut(reg["drop"], 0)
+        out["dropout_masks"] = reg.get("dropout_masks", False)
         return out
     model.sample_regularisers = sliced
     opt = mgr.fusion_optimizer(model)

@@ -73,8 +73,13 @@ def test_row_shift_split(cuda):
                                            (300, 30, 20, 300, 1), (256, 16, 1000, 500, 8),
                                            (1000, 200, 1600, 100, 8), (768, 128, 40, 500, 8), (1300, 650, 600, 300, 8),
                                            (900, 300, 1000, 500, 1)])
-def test_fused_prologue_projection(cuda, BT, T, F, H, nvar):
-    """gr_gemm_a32_f32, transA=0: P[:, v*H:(v+1)*H] = (X o mask_v) W_v + b with X read as fp32."""
+@pytest.mark.parametrize("mask_scale", [0.0, 2.0])
+def test_fused_prologue_projection(cuda, BT, T, F, H, nvar, mask_scale):
+    """gr_gemm_a32_f32, transA=0: P[:, v*H:(v+1)*H] = (X o mask_v) W_v + b with X read as fp32.
+    mask_scale = 2: the same masks declared as dropout masks {0, 2} (gr_gemm_a32_dropout_f32: one split per tile
+    shared by four variants, scale in the epilogue) -- same tolerance against the fp64 product."""
+    if mask_scale and nvar != 8:
+        pytest.skip("no masks")
     from mgr_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(BT + F)
     X = torch.randn(BT, F, generator=g).to(cuda)
@@ -84,7 +89,8 @@ def test_fused_prologue_projection(cuda, BT, T, F, H, nvar):
     masks = ((torch.rand(nvar, BT // T, F, generator=g) > 0.5).float() * 2).to(cuda) if nvar == 8 else None
     w_hi, w_lo = ops.split_bf16(W, transpose=True)
     out = torch.empty(BT, nvar * Nv, device=cuda)
-    ops.gemm_a32(X, w_hi, w_lo, BT, Nv, F, out, nvar * Nv, nvar=nvar, mask=masks, rows_per_seq=T, bias=bias)
+    ops.gemm_a32(X, w_hi, w_lo, BT, Nv, F, out, nvar * Nv, nvar=nvar, mask=masks, rows_per_seq=T, bias=bias,
+                 mask_scale=mask_scale)
     torch.cuda.synchronize()
     Xd, Wd = X.double(), W.double()
     if masks is None:
@@ -97,9 +103,14 @@ def test_fused_prologue_projection(cuda, BT, T, F, H, nvar):
 
 @pytest.mark.parametrize("BT,T,F,H,masked", [(256, 32, 64, 32, True), (1024, 64, 1600, 100, True), (600, 50, 39, 24, False),
                                              (4096, 128, 200, 100, True), (3000, 1000, 1600, 100, True),
-                                             (2000, 100, 77, 36, True), (1500, 500, 600, 300, False)])
-def test_fused_prologue_weight_gradient(cuda, BT, T, F, H, masked):
-    """transA=1: dW_v = (X o mask_v)^T dP_v (split-K, atomics) and the shifted dU contraction."""
+                                             (2000, 100, 77, 36, True), (1500, 500, 600, 300, False),
+                                             (5000, 1000, 1600, 100, True), (4224, 66, 200, 100, True)])
+@pytest.mark.parametrize("mask_scale", [0.0, 2.0])
+def test_fused_prologue_weight_gradient(cuda, BT, T, F, H, masked, mask_scale):
+    """transA=1: dW_v = (X o mask_v)^T dP_v (split-K, atomics) and the shifted dU contraction; mask_scale = 2: the
+    masks declared as dropout masks (shared split, keep bits; T = 66 / 1000 put sequence ends inside 8-row chunks)."""
+    if mask_scale and not masked:
+        pytest.skip("no masks")
     from mgr_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(BT + F + 1)
     X = torch.randn(BT, F, generator=g).to(cuda)
@@ -108,7 +119,8 @@ def test_fused_prologue_weight_gradient(cuda, BT, T, F, H, masked):
     pt_hi, pt_lo = ops.split_bf16(dP, transpose=True)
     dW = torch.empty(F, 8 * H, device=cuda)
     if masked:
-        ops.gemm_a32(X, pt_hi, pt_lo, F, H, BT, dW, 8 * H, nvar=8, mask=masks, rows_per_seq=T, transA=True)
+        ops.gemm_a32(X, pt_hi, pt_lo, F, H, BT, dW, 8 * H, nvar=8, mask=masks, rows_per_seq=T, transA=True,
+                     mask_scale=mask_scale)
         ref = torch.cat([(X.double().reshape(-1, T, F) * masks[v].double()[:, None, :]).reshape(BT, F).T
                          @ dP.double()[:, v * H:(v + 1) * H] for v in range(8)], 1)
     else:
@@ -138,13 +150,13 @@ def test_projection_variant_grouping(cuda, monkeypatch, nvg):
     """Both tile schedules of the fused projection (one variant per CTA / four variants sharing one
     loaded A tile, GR_A32_NVG) give the same parity, row-major and transposed."""
     monkeypatch.setenv("GR_A32_NVG", nvg)
-    test_fused_prologue_projection(cuda, 384, 48, 1600, 100, 8)
-    test_fused_prologue_projection(cuda, 1000, 200, 1600, 100, 8)
-    test_fused_prologue_weight_gradient(cuda, 384, 96, 1600, 100, True)
+    test_fused_prologue_projection(cuda, 384, 48, 1600, 100, 8, 0.0)
+    test_fused_prologue_projection(cuda, 1000, 200, 1600, 100, 8, 0.0)
+    test_fused_prologue_weight_gradient(cuda, 384, 96, 1600, 100, True, 0.0)
 
 
 def test_projection_epilogue_variants(cuda, monkeypatch):
     """The TMA-store epilogue and the st.global cross-check epilogue (GR_A32_EPI=stg) agree with fp64."""
     monkeypatch.setenv("GR_A32_EPI", "stg")
-    test_fused_prologue_projection(cuda, 256, 16, 1000, 500, 8)
-    test_fused_prologue_projection(cuda, 768, 128, 40, 500, 8)
+    test_fused_prologue_projection(cuda, 256, 16, 1000, 500, 8, 0.0)
+    test_fused_prologue_projection(cuda, 768, 128, 40, 500, 8, 0.0)
