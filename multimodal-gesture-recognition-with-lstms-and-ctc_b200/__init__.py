@@ -11,5 +11,6 @@ from .layers import BidirectionalLSTM, DenseSoftmax, blstm  # noqa: F401
 from .models import (SpeechNet, SkeletalNet, FusionNet, UnimodalNet, KerasAdam, fusion_optimizer,  # noqa: F401
                      FusionTrainer)
 from .sequence_decoding import decode_batch, decode_batch_speech, decode_ids, ctc_decode  # noqa: F401
+from . import custom_ops  # noqa: F401  (registers torch.ops.mgr_b200.*)
 
 __version__ = "0.1.0"
