@@ -429,12 +429,15 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
       }
     } else if constexpr (MODE == 2) {
       // ---------------- fast transposed producer ----------------
-      // warp w <-> tile rows (m) 16w..16w+15; lane = kc*4 + mq: k rows 8kc..8kc+7 of the k-block (one
+      // warp w <-> tile rows (m) 16w..16w+15; lane = (mq, kc): k rows 8kc..8kc+7 of the k-block (one
       // 16-byte chunk of each output row) x the float4 of m = 16w + 4mq..+3.  Loads are 128-bit
       // (8 per thread per k-block instead of 32 scalar ones, which capped the SM's requests in
-      // flight); stores are STS.128 with 2-way bank conflicts.
+      // flight); stores are STS.128.
       const int w = t >> 5, ln = t & 31;
-      const int kc = ln >> 2, mq = ln & 3;
+      // lane = mq*8 + kc: the 8 lanes of a quarter-warp (one STS.128 wavefront) share a tile row and cover its 8 swizzled
+      // 16-byte chunks -- conflict-free (kc*4 + mq put two rows 8 apart on the same banks: 2-way conflicts, ncu:
+      // 106 M wavefronts for 53 M ideal in the fusion dW); the global loads touch the same addresses as before
+      const int kc = ln & 7, mq = ln >> 3;
       const int T_ = p.rows_per_seq;
       const int nseq = (p.K + T_ - 1) / T_;
       const int rloc = 16 * w + 4 * mq;              // first tile row of this thread
