@@ -129,13 +129,15 @@ __global__ void __launch_bounds__(128) dense_softmax_fwd_row_kernel(const float*
 }
 
 // ------------------------------------------------------------------ Dense backward
-// thread <-> input feature k; C accumulators (dWd[k,:]) and W[k,:] in registers; rows tiled by 32.
+// thread <-> input feature k; C accumulators (dWd[k,:]) and W[k,:] in registers; rows tiled by 32.  The row loop is
+// unrolled by four with all x / mask loads issued first (one load pair in flight per thread left the kernel latency-bound
+// at 0.9 TB/s: 0.71 ms for the fusion head), and the staged gradients are zero-padded to CR columns and read as float4.
 template <int CR>
 __global__ void __launch_bounds__(256) dense_bwd_kernel(const float* __restrict__ x, const float* __restrict__ mask,
                                                        const float* __restrict__ Wd, const float* __restrict__ g,
                                                        int R, int Fin, int C, int rows_per_cta, float* __restrict__ dWd,
                                                        float* __restrict__ dbd, float* __restrict__ dx) {
-  __shared__ float gs[32][kCMax];
+  __shared__ __align__(16) float gs[32][CR];
   const int r_begin = blockIdx.x * rows_per_cta;
   const int r_end = min(R, r_begin + rows_per_cta);
   if (r_begin >= r_end) return;
@@ -149,24 +151,40 @@ __global__ void __launch_bounds__(256) dense_bwd_kernel(const float* __restrict_
     for (int r0 = r_begin; r0 < r_end; r0 += 32) {
       const int nr = min(32, r_end - r0);
       __syncthreads();
-      for (int e = threadIdx.x; e < nr * C; e += blockDim.x) gs[e / C][e % C] = g[(size_t)r0 * C + e];
+      for (int e = threadIdx.x; e < nr * CR; e += blockDim.x) {
+        const int rr = e / CR, c = e - rr * CR;
+        gs[rr][c] = c < C ? g[(size_t)(r0 + rr) * C + c] : 0.f;
+      }
       __syncthreads();
       if (kbase == 0 && threadIdx.x < C)
         for (int r = 0; r < nr; ++r) accb += gs[r][threadIdx.x];
       if (kok) {
-        for (int r = 0; r < nr; ++r) {
-          const size_t off = (size_t)(r0 + r) * Fin + k;
-          const float mv = mask ? mask[off] : 1.f;
-          const float xv = x[off] * mv;
-          float d = 0.f;
+        for (int r = 0; r < nr; r += 4) {
+          float xv[4], mv[4];
 #pragma unroll
-          for (int c = 0; c < CR; ++c)
-            if (c < C) {
-              const float gv = gs[r][c];
-              acc[c] = fmaf(xv, gv, acc[c]);
-              d = fmaf(gv, w[c], d);
+          for (int u = 0; u < 4; ++u) {
+            const bool ok = r + u < nr;
+            const size_t off = (size_t)(r0 + r + u) * Fin + k;
+            mv[u] = ok ? (mask ? mask[off] : 1.f) : 0.f;
+            xv[u] = ok ? x[off] : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (r + u < nr) {
+              const float xm = xv[u] * mv[u];
+              const float4* g4 = reinterpret_cast<const float4*>(gs[r + u]);
+              float d = 0.f;
+#pragma unroll
+              for (int c4 = 0; c4 < CR / 4; ++c4) {
+                const float4 gq = g4[c4];
+                acc[4 * c4] = fmaf(xm, gq.x, acc[4 * c4]);         d = fmaf(gq.x, w[4 * c4], d);
+                acc[4 * c4 + 1] = fmaf(xm, gq.y, acc[4 * c4 + 1]); d = fmaf(gq.y, w[4 * c4 + 1], d);
+                acc[4 * c4 + 2] = fmaf(xm, gq.z, acc[4 * c4 + 2]); d = fmaf(gq.z, w[4 * c4 + 2], d);
+                acc[4 * c4 + 3] = fmaf(xm, gq.w, acc[4 * c4 + 3]); d = fmaf(gq.w, w[4 * c4 + 3], d);
+              }
+              if (dx) dx[(size_t)(r0 + r + u) * Fin + k] = d * mv[u];
             }
-          if (dx) dx[off] = d * mv;
+          }
         }
       }
     }
@@ -360,7 +378,9 @@ extern "C" int gr_dense_bwd_f32(const float* x, const float* drop_mask, const fl
   int rows_per_cta = (R + ctas - 1) / ctas;
   rows_per_cta = (rows_per_cta + 31) / 32 * 32;
   const int grid = (R + rows_per_cta - 1) / rows_per_cta;
-  if (C <= 32) dense_bwd_kernel<32><<<grid, 256, 0, s>>>(x, drop_mask, Wd, g_logits, R, Fin, C, rows_per_cta, dWd, dbd, dx);
+  if (C <= 24) dense_bwd_kernel<24><<<grid, 256, 0, s>>>(x, drop_mask, Wd, g_logits, R, Fin, C, rows_per_cta, dWd, dbd, dx);
+  else if (C <= 32) dense_bwd_kernel<32><<<grid, 256, 0, s>>>(x, drop_mask, Wd, g_logits, R, Fin, C, rows_per_cta, dWd, dbd, dx);
+  else if (C <= 44) dense_bwd_kernel<44><<<grid, 256, 0, s>>>(x, drop_mask, Wd, g_logits, R, Fin, C, rows_per_cta, dWd, dbd, dx);
   else dense_bwd_kernel<64><<<grid, 256, 0, s>>>(x, drop_mask, Wd, g_logits, R, Fin, C, rows_per_cta, dWd, dbd, dx);
   GR_CHECK_LAUNCH("dense_bwd_kernel");
   return GR_OK;

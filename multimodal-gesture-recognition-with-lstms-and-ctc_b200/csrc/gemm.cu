@@ -235,6 +235,44 @@ __global__ void split_bf16_t_kernel(const float* __restrict__ x, const float* __
   }
 }
 
+// plain transposing split (no mask, no shift) in 64 x 64 tiles: 256-byte row pieces in, bf16x2 pairs out (128 bytes per
+// warp and output row).  The 32 x 32 tile kernel above moved the fusion layer's dP (256000 x 800) at 2 TB/s (0.80 ms):
+// 200 k CTAs of one 4 KB tile each, 64-byte output pieces.
+__global__ void __launch_bounds__(256) split_bf16_t64_kernel(const float* __restrict__ x, int R, int K, int ldx,
+                                                             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                             int ld_out) {
+  __shared__ float tileT[64][65];      // [k][r]
+  const int r0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const bool kvec = (ldx % 2) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0;
+#pragma unroll
+  for (int i = ty; i < 64; i += 8) {
+    const int r = r0 + i, k = k0 + 2 * tx;
+    float2 v = make_float2(0.f, 0.f);
+    if (r < R) {
+      const float* src = x + (size_t)r * ldx + k;
+      if (kvec && k + 1 < K) v = *reinterpret_cast<const float2*>(src);
+      else { if (k < K) v.x = src[0]; if (k + 1 < K) v.y = src[1]; }
+    }
+    tileT[2 * tx][i] = v.x;
+    tileT[2 * tx + 1][i] = v.y;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = ty; i < 64; i += 8) {
+    const int k = k0 + i, r = r0 + 2 * tx;
+    if (k < K && r < ld_out) {           // ld_out is even: r + 1 < ld_out as well
+      const float a = tileT[i][2 * tx], b = tileT[i][2 * tx + 1];
+      const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      *reinterpret_cast<__nv_bfloat162*>(hi + (size_t)k * ld_out + r) = h;
+      if (lo) {
+        const float2 hf = __bfloat1622float2(h);
+        *reinterpret_cast<__nv_bfloat162*>(lo + (size_t)k * ld_out + r) = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+      }
+    }
+  }
+}
+
 // host-side launcher used by other translation units (lstm_tc.cu: one-time split of U)
 int split_bf16_t_launch(const float* x, int R, int K, int ldx, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_out,
                         cudaStream_t s) {
@@ -343,9 +381,16 @@ extern "C" int gr_split_bf16_f32(const float* x, const float* add, const float* 
   } else {
     if (ld_out < R) return set_error(GR_EINVAL, "split_bf16: ld_out < R (transpose)");
     if (add || noise) return set_error(GR_EUNSUPPORTED, "split_bf16: add/noise with transpose");
+    const bool out_al = (ld_out % 2) == 0 && ((reinterpret_cast<uintptr_t>(out_hi) | reinterpret_cast<uintptr_t>(out_lo)) & 3) == 0;
+    if (!mask && row_shift == 0 && out_al && (size_t)R * K >= (size_t)1 << 20) {
+      dim3 grid((ld_out + 63) / 64, (K + 63) / 64);
+      split_bf16_t64_kernel<<<grid, 256, 0, s>>>(x, R, K, ldx, static_cast<__nv_bfloat16*>(out_hi),
+                                                 static_cast<__nv_bfloat16*>(out_lo), ld_out);
+    } else {
     dim3 grid((ld_out + 31) / 32, (K + 31) / 32), block(32, 8);
     split_bf16_t_kernel<<<grid, block, 0, s>>>(x, mask, rows_per_seq, R, K, ldx, row_shift, static_cast<__nv_bfloat16*>(out_hi),
                                               static_cast<__nv_bfloat16*>(out_lo), ld_out);
+    }
   }
   GR_CHECK_LAUNCH("split_bf16_kernel");
   return GR_OK;

@@ -35,7 +35,9 @@ class UnimodalNet(nn.Module):
         """Keras depth-sorted layer list as multimodal.py:109-118 indexes it."""
         return [None, None, self.blstm_1, self.blstm_2]
 
-    def sample_regularisers(self, B, T, seed, step, device):
+    def sample_regularisers(self, B, T, seed, step, device, head=True):
+        """`head=False`: the tower only (no Dropout mask for the uni-modal Dense head -- the fusion model drops that
+        head, multimodal.py:109-118, and drawing the (B,T,2H) mask anyway cost 1.6 GB of writes per step)."""
         reg = {}
         off = int(step) * 64
         if self.noise_std > 0:
@@ -44,7 +46,7 @@ class UnimodalNet(nn.Module):
             reg["m1"] = ops.dropout_mask((8, B, self.numfeats), self.p1, seed + 1, off, device)
         if self.p2 > 0:
             reg["m2"] = ops.dropout_mask((8, B, 2 * self.units), self.p2, seed + 2, off, device)
-        if self.pd > 0:
+        if self.pd > 0 and head:
             reg["drop"] = ops.dropout_mask((B, T, 2 * self.units), self.pd, seed + 3, off, device)
         reg["dropout_masks"] = True    # m1 / m2 hold only 0 and 1/(1-p): see BidirectionalLSTM.forward
         return reg
@@ -120,10 +122,8 @@ class FusionNet(nn.Module):
     def sample_regularisers(self, B, T, seed, step, device):
         off = int(step) * 64
         reg = {"sp": {}, "sk": {}}
-        sp = self.speech.sample_regularisers(B, T, seed + 10, step, device)
-        sk = self.skeletal.sample_regularisers(B, T, seed + 20, step, device)
-        sp.pop("drop", None)
-        sk.pop("drop", None)
+        sp = self.speech.sample_regularisers(B, T, seed + 10, step, device, head=False)
+        sk = self.skeletal.sample_regularisers(B, T, seed + 20, step, device, head=False)
         sk.pop("noise", None)  # GaussianNoise(0.0) on the skeletal branch (multimodal.py:105)
         reg["sp"], reg["sk"] = sp, sk
         reg["m3"] = ops.dropout_mask((8, B, self.blstm_3.input_dim), self.blstm_3.dropout, seed + 30, off, device)
