@@ -125,6 +125,17 @@ int gr_lstm_workspace_bytes(int B, int H, size_t* bytes_out);
 int gr_lstm_recurrence_fwd_f32(float* gates, const float* U, int B, int T, int H, float* y,
                                float* cell /* may be NULL: inference, c_t not kept */,
                                void* workspace, size_t workspace_bytes, void* stream);
+/* The same forward recurrence with an AUXILIARY destination for h: `aux` points at the first of 2H consecutive columns of a
+ * (B*T, ld_aux) fp32 matrix -- e.g. this tower's block of the fusion model's Merge(concat) buffer (multimodal.py:155-156).
+ * accumulate == 0: h is stored there as well; accumulate != 0: h is ADDED to what is there (TMA reduce-add), which is how the
+ * residual `add([blstm_1, blstm_2])` (speech_lstm_ctc_words.py:79, multimodal.py:119-133) lands in the concat buffer with no
+ * separate pass: layer 1 stores, layer 2 accumulates.  y may be NULL (h is then written to aux only); cell as above.
+ * Only the tensor-memory kernel of the wide layers has this output: gr_lstm_recurrence_aux_supported(B, H) != 0,
+ * else GR_EUNSUPPORTED.  aux, ld_aux and H must keep 16-byte alignment. */
+int gr_lstm_recurrence_aux_supported(int B, int H);
+int gr_lstm_recurrence_fwd_aux_f32(float* gates, const float* U, int B, int T, int H, float* y, float* cell,
+                                   float* aux, int ld_aux, int accumulate, void* workspace,
+                                   size_t workspace_bytes, void* stream);
 int gr_lstm_recurrence_bwd_f32(float* gates /* in: i,f,g,o ; out: dP */, const float* cell,
                                const float* dy, const float* U, int B, int T, int H,
                                void* workspace, size_t workspace_bytes, void* stream);

@@ -41,6 +41,8 @@ _SIGNATURES = {
                         c_int),
     "gr_lstm_workspace_bytes": ([c_int, c_int, ctypes.POINTER(c_size_t)], c_int),
     "gr_lstm_recurrence_fwd_f32": ([_P, _P, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P], c_int),
+    "gr_lstm_recurrence_aux_supported": ([c_int, c_int], c_int),
+    "gr_lstm_recurrence_fwd_aux_f32": ([_P, _P, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, _P, c_size_t, _P], c_int),
     "gr_lstm_recurrence_bwd_f32": ([_P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P], c_int),
     "gr_gemm_bf16x3_f32": ([_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],
                            c_int),
@@ -121,7 +123,7 @@ def note_work(amount):
 
 
 # entry points that are timed under another entry point's name (same kernel family)
-_TIMING_ALIAS = {"gr_gemm_a32_dropout_f32": "gr_gemm_a32_f32"}
+_TIMING_ALIAS = {"gr_gemm_a32_dropout_f32": "gr_gemm_a32_f32", "gr_lstm_recurrence_fwd_aux_f32": "gr_lstm_recurrence_fwd_f32"}
 
 
 def call(name, *args):

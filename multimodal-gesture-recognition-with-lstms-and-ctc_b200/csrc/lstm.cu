@@ -287,7 +287,7 @@ bool lstm_tcu_supported(int B, int H);
 size_t lstm_tcu_workspace_bytes(int B, int H);
 size_t lstm_tcu_trace_offset(int B, int H);
 int lstm_fwd_tcu_launch(float* gates, const float* U, int B, int T, int H, float* y, float* cell, void* workspace,
-                        cudaStream_t s);
+                        cudaStream_t s, float* aux = nullptr, int ld_aux = 0, int aux_mode = 0);
 
 bool lstm_tcu_bwd_supported(int B, int H);
 size_t lstm_tcu_bwd_workspace_bytes(int B, int H);
@@ -386,6 +386,27 @@ extern "C" int gr_lstm_recurrence_fwd_f32(float* gates, const float* U, int B, i
   void* args[] = {&p};
   GR_CUDA(cudaLaunchCooperativeKernel((void*)lstm_fwd_kernel, dim3(2 * p.UG), dim3(kLstmThreads), args, smem, s));
   return GR_OK;
+}
+
+extern "C" int gr_lstm_recurrence_aux_supported(int B, int H) {
+  return (!gr::lstm_small_supported(H) && gr::use_tcu_path(B, H)) ? 1 : 0;
+}
+
+extern "C" int gr_lstm_recurrence_fwd_aux_f32(float* gates, const float* U, int B, int T, int H, float* y, float* cell,
+                                              float* aux, int ld_aux, int accumulate, void* workspace,
+                                              size_t workspace_bytes, void* stream) {
+  using namespace gr;
+  if (!gates || !U || !aux || !workspace) return set_error(GR_EINVAL, "lstm_fwd_aux: null pointer");
+  if (B <= 0 || T <= 0 || H <= 0 || ld_aux < 2 * H) return set_error(GR_EINVAL, "lstm_fwd_aux: bad shape");
+  if ((ld_aux % 4) || (H % 4) || (reinterpret_cast<uintptr_t>(aux) & 15))
+    return set_error(GR_EUNSUPPORTED, "lstm_fwd_aux: aux, ld_aux and H must be 16-byte aligned");
+  if (!gr_lstm_recurrence_aux_supported(B, H))
+    return set_error(GR_EUNSUPPORTED, "lstm_fwd_aux: only the tensor-memory recurrence (wide layers) has the auxiliary output");
+  size_t need = 0;
+  gr_lstm_workspace_bytes(B, H, &need);
+  if (workspace_bytes < need) return set_error(GR_EWORKSPACE, "lstm_fwd_aux: workspace too small");
+  return lstm_fwd_tcu_launch(gates, U, B, T, H, y, cell, workspace, static_cast<cudaStream_t>(stream), aux, ld_aux,
+                             accumulate ? 2 : 1);
 }
 
 extern "C" int gr_lstm_recurrence_bwd_f32(float* gates, const float* cell, const float* dy,

@@ -47,6 +47,8 @@ struct LstmTcuParams {
   const __nv_bfloat16* ut_lo;
   long long* trace;
   int B, T, H, Bpad, UGn, NTg, NSB, Kc, KS, Kp8, CP, NREQ, save;
+  int store_y;                 // 0: y is not written (inference with an auxiliary destination only)
+  int aux_mode;                // 0 none, 1: h tiles are ALSO stored to the auxiliary tensor, 2: reduce-added to it (TMA .add)
   int dbg;                     // GR_TCU_DBG experiments: 1 = MMAs of the next tile are NOT held back behind the epilogue's tcgen05.ld, 2 = no MMAs, 4 = no h loads
 };
 
@@ -69,6 +71,11 @@ __device__ __forceinline__ void tma_load_4d_u(void* dst, const CUtensorMap* tm, 
 }
 __device__ __forceinline__ void tma_store_4d_u(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// shared -> global tile ADDED to the destination (fp32 add performed at the memory side)
+__device__ __forceinline__ void tma_reduce_add_4d_u(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ bool elect_one_u() {
@@ -112,7 +119,8 @@ __device__ __forceinline__ void tmem_st_zero_32x8(uint32_t taddr) {
 template <int NB, int NT>
 __global__ void __launch_bounds__(kUThreads, 1)
 lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmG,
-                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmC, LstmTcuParams p) {
+                    const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmC,
+                    const __grid_constant__ CUtensorMap tmA, LstmTcuParams p) {
   constexpr int X = NB / 16;                    // 8-column groups per epilogue warp (each warp: NB/2 columns)
   // Narrow tiles: ONE MMA per k-step with N = 2 NB over the stacked [h_hi rows ; h_lo rows] slabs (they are adjacent
   // in the stage), D columns [0, NB) = A h_hi^T and [NB, 2NB) = A h_lo^T, added in the epilogue.  At N = 16 / 32 the
@@ -153,6 +161,7 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmG)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     for (int s = 0; s < kURing; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 4; ++s) mbar_init(&tmem_full[s], 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&p_full[s], 1); mbar_init(&stage_ready[s], kUEpi); }
@@ -476,7 +485,11 @@ lstm_fwd_tcu_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_consta
         const int t = dir == 0 ? s : T - 1 - s;
         const int b0 = (NT * sb + tau) * NB;
         mbar_wait(&stage_ready[slot], (uint32_t)(n >> 1) & 1u);
-        tma_store_4d_u(&tmY, io + kIo, j0, b0, t, dir);
+        if (p.store_y) tma_store_4d_u(&tmY, io + kIo, j0, b0, t, dir);
+        // auxiliary destination (the fusion model's Merge(concat) buffer): layer 1 of a tower stores its h there as well,
+        // layer 2 ADDS its h (residual `add`, speech_lstm_ctc_words.py:79) -- no separate add pass over (B,T,2H)
+        if (p.aux_mode == 1) tma_store_4d_u(&tmA, io + kIo, j0, b0, t, dir);
+        else if (p.aux_mode == 2) tma_reduce_add_4d_u(&tmA, io + kIo, j0, b0, t, dir);
         if (p.save) {
           tma_store_4d_u(&tmC, io + kIo + kYs, j0, b0, t, dir);
           tma_store_4d_u(&tmG, io, j0, b0, t, dir * 4);
@@ -968,11 +981,13 @@ static int make_io_map_u(CUtensorMap* tm, const float* base, int B, int T, int H
 }
 
 int lstm_fwd_tcu_launch(float* gates, const float* U, int B, int T, int H, float* y, float* cell, void* workspace,
-                        cudaStream_t s) {
+                        cudaStream_t s, float* aux, int ld_aux, int aux_mode) {
   TcuLayout L = tcu_layout(B, H);
   char* w = static_cast<char*>(workspace);
   LstmTcuParams p;
   p.save = cell != nullptr;
+  p.store_y = y != nullptr;
+  p.aux_mode = aux ? aux_mode : 0;
   p.hx = reinterpret_cast<uint8_t*>(w + L.off_hx);
   p.counters = reinterpret_cast<unsigned*>(w);
   p.dbg = getenv("GR_TCU_DBG") ? atoi(getenv("GR_TCU_DBG")) : 0;
@@ -999,9 +1014,20 @@ int lstm_fwd_tcu_launch(float* gates, const float* U, int B, int T, int H, float
       return rc;
   }
   if ((rc = make_io_map_u(&tG, gates, B, T, H, 8, L.NB, 4)) != GR_OK) return rc;
-  if ((rc = make_io_map_u(&tY, y, B, T, H, 2, L.NB, 1)) != GR_OK) return rc;
-  if ((rc = make_io_map_u(&tC, cell ? cell : y, B, T, H, 2, L.NB, 1)) != GR_OK) return rc;
-  void* args[] = {&tH, &tG, &tY, &tC, &p};
+  CUtensorMap tA;
+  if (aux) {
+    // (unit, batch row, time, direction) view of columns [0, 2H) of a (B*T, ld_aux) matrix starting at `aux`
+    const cuuint64_t dims[4] = {(cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)T, 2};
+    const cuuint64_t strides[3] = {(cuuint64_t)T * ld_aux * 4, (cuuint64_t)ld_aux * 4, (cuuint64_t)H * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)kUUnits, (cuuint32_t)L.NB, 1, 1};
+    if ((rc = make_map_nd(&tA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, aux, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) != GR_OK)
+      return rc;
+  }
+  float* ymap = y ? y : (cell ? cell : gates);     // any valid base: the map is not used when y is not stored
+  if ((rc = make_io_map_u(&tY, ymap, B, T, H, 2, L.NB, 1)) != GR_OK) return rc;
+  if ((rc = make_io_map_u(&tC, cell ? cell : ymap, B, T, H, 2, L.NB, 1)) != GR_OK) return rc;
+  if (!aux) tA = tY;
+  void* args[] = {&tH, &tG, &tY, &tC, &tA, &p};
   const dim3 grid(2 * L.NSB * L.UGn), block(kUThreads);
   auto go = [&](auto kern) -> int {
     GR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));

@@ -104,6 +104,21 @@ class _BlstmFn(torch.autograd.Function):
         return dx, dW, dU, db, None, None, None
 
 
+def blstm_into(x, W, U, b, masks, mask_scale, aux, col0, accumulate, want_y):
+    """Inference-only BLSTM whose output ALSO lands in columns [col0, col0 + 2H) of `aux` (B,T,Fo): stored, or added to
+    what is there (`accumulate`).  Returns y, or None with `want_y=False`.  Used by the frozen towers of the fusion
+    model: layer 1 stores into the Merge(concat) buffer, layer 2 accumulates -- the residual add costs no extra pass."""
+    B, T, F = x.shape
+    H = U.shape[1]
+    with torch.no_grad():
+        x, W, U, b = x.contiguous(), W.contiguous(), U.contiguous(), b.contiguous()
+        masks = None if masks is None else masks.contiguous()
+        gates = _project(x.reshape(B * T, F), W, b, masks, B, T, H, mask_scale=mask_scale)
+        y, _ = ops.lstm_recurrence_fwd(gates, U, B, T, H, keep_cell=False, aux=aux, aux_col0=col0,
+                                       aux_accumulate=accumulate, want_y=want_y)
+    return y
+
+
 def blstm(x, W, U, b, masks=None, passes=None, mask_scale=0.0):
     """Functional form.  W (F,8H) = [fwd kernel | bwd kernel]; U (2,H,4H); b (8H);
     masks None or (8, B, F): input-dropout masks for (dir, gate) = (0,i),(0,f),(0,c),(0,o),(1,i)..;
@@ -175,6 +190,14 @@ class BidirectionalLSTM(nn.Module):
         if self.dropout <= 0.0:
             return None
         return ops.dropout_mask((8, B, self.input_dim), self.dropout, seed, offset, self.kernel.device)
+
+    def _scale(self, masks, dropout_masks):
+        return 1.0 / (1.0 - self.dropout) if (dropout_masks and masks is not None and 0.0 < self.dropout < 1.0) else 0.0
+
+    def forward_into(self, x, masks, dropout_masks, aux, col0, accumulate, want_y=True):
+        """No-grad forward that also stores / accumulates the output into `aux[..., col0:col0+2*units]` (see blstm_into)."""
+        return blstm_into(x, self.kernel, self.recurrent_kernel, self.bias, masks, self._scale(masks, dropout_masks), aux,
+                          col0, accumulate, want_y)
 
     def forward(self, x, masks=None, dropout_masks=False):
         """`dropout_masks=True`: `masks` came from `make_masks` / `ops.dropout_mask` with this layer's rate, i.e. every

@@ -58,6 +58,12 @@ class UnimodalNet(nn.Module):
         if reg.get("noise") is not None:
             x = ops.add(x, reg["noise"])
         dm = bool(reg.get("dropout_masks", False))
+        if (merged is not None and not torch.is_grad_enabled() and os.environ.get("GR_TOWER_AUX", "1") != "0"
+                and ops.lstm_aux_supported(x.shape[0], self.units) and merged.is_contiguous() and col0 % 4 == 0):
+            # the recurrences write the residual sum themselves: layer 1 stores h into the concat block, layer 2 adds its h
+            y1 = self.blstm_1.forward_into(x, reg.get("m1"), dm, merged, col0, accumulate=False)
+            self.blstm_2.forward_into(y1, reg.get("m2"), dm, merged, col0, accumulate=True, want_y=False)
+            return merged
         y1 = self.blstm_1(x, reg.get("m1"), dm)
         y2 = self.blstm_2(y1, reg.get("m2"), dm)
         if merged is not None:

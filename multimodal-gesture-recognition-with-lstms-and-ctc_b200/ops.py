@@ -169,13 +169,27 @@ def lstm_workspace(B, H, device):
     return _workspace("lstm", nbytes.value, device)
 
 
-def lstm_recurrence_fwd(gates, U, B, T, H, keep_cell=True):
-    require_cuda(gates, U)
-    y = torch.empty((B, T, 2 * H), dtype=torch.float32, device=gates.device)
+def lstm_aux_supported(B, H):
+    """True when the recurrence of this shape can write / accumulate h into an auxiliary (B,T,ld) buffer."""
+    return bool(_lib.load().gr_lstm_recurrence_aux_supported(int(B), int(H)))
+
+
+def lstm_recurrence_fwd(gates, U, B, T, H, keep_cell=True, aux=None, aux_col0=0, aux_accumulate=False, want_y=True):
+    """`aux`: (B, T, Fo) buffer whose columns [aux_col0, aux_col0 + 2H) also receive h (stored, or added when
+    `aux_accumulate`); with `want_y=False` no separate y tensor is written (returns y = None)."""
+    import ctypes
+    require_cuda(gates, U, aux)
+    y = torch.empty((B, T, 2 * H), dtype=torch.float32, device=gates.device) if (want_y or aux is None) else None
     cell = torch.empty((B, T, 2 * H), dtype=torch.float32, device=gates.device) if keep_cell else None
     ws = lstm_workspace(B, H, gates.device)
     # algorithmic bytes (SURVEY 8d): read 4H pre-activations, write h (+ 4H gates + c when kept)
     _lib.note_work(float(B) * T * 2 * H * (40 if keep_cell else 20))
+    if aux is not None:
+        assert aux.dim() == 3 and aux.shape[0] == B and aux.shape[1] == T and aux.is_contiguous()
+        aptr = ctypes.c_void_p(aux.data_ptr() + 4 * int(aux_col0))
+        call("gr_lstm_recurrence_fwd_aux_f32", ptr(gates), ptr(U), B, T, H, ptr(y), ptr(cell), aptr, int(aux.shape[2]),
+             int(bool(aux_accumulate)), ptr(ws), ws.numel(), stream_ptr())
+        return y, cell
     call("gr_lstm_recurrence_fwd_f32", ptr(gates), ptr(U), B, T, H, ptr(y), ptr(cell), ptr(ws), ws.numel(),
          stream_ptr())
     return y, cell

@@ -224,3 +224,47 @@ def test_tensor_core_bptt_matches_generic_and_is_deterministic(cuda, monkeypatch
     d_tc2 = ops.lstm_recurrence_bwd(gates.clone(), cell, dy, U, B, T, H).clone()
     assert torch.equal(d_tc, d_tc2)
     assert (d_tc - d_gen).abs().max().item() <= 1e-4 * d_gen.abs().max().item()
+
+
+@pytest.mark.parametrize("B,T,H", [(5, 12, 128), (40, 9, 300), (130, 6, 500)])
+def test_recurrence_auxiliary_output(cuda, B, T, H):
+    """gr_lstm_recurrence_fwd_aux_f32: h is also stored into / added to a column block of a wider (B,T,Fo) buffer
+    (the towers' residual add written straight into the Merge(concat) buffer) -- bit-equal to y and to prior + y."""
+    from mgr_b200 import ops
+    if not ops.lstm_aux_supported(B, H):
+        pytest.skip("tensor-memory recurrence not available for this shape")
+    g = torch.Generator().manual_seed(B + H)
+    gates = (torch.randn(B * T, 8 * H, generator=g) * 0.5).to(cuda)
+    U = (torch.randn(2, H, 4 * H, generator=g) / H ** 0.5).to(cuda)
+    y_ref, _ = ops.lstm_recurrence_fwd(gates.clone(), U, B, T, H, keep_cell=False)
+    Fo, col0 = 2 * H + 24, 8
+    prior = torch.randn(B, T, Fo, generator=g).to(cuda)
+    buf = prior.clone()
+    y1, _ = ops.lstm_recurrence_fwd(gates.clone(), U, B, T, H, keep_cell=False, aux=buf, aux_col0=col0)
+    assert torch.equal(y1, y_ref)
+    assert torch.equal(buf[:, :, col0:col0 + 2 * H], y_ref)
+    assert torch.equal(buf[:, :, :col0], prior[:, :, :col0]) and torch.equal(buf[:, :, col0 + 2 * H:], prior[:, :, col0 + 2 * H:])
+    buf2 = prior.clone()
+    y2, cell = ops.lstm_recurrence_fwd(gates.clone(), U, B, T, H, keep_cell=True, aux=buf2, aux_col0=col0, aux_accumulate=True,
+                                       want_y=False)
+    assert y2 is None and cell is not None
+    assert torch.equal(buf2[:, :, col0:col0 + 2 * H], prior[:, :, col0:col0 + 2 * H] + y_ref)
+    assert torch.equal(buf2[:, :, :col0], prior[:, :, :col0]) and torch.equal(buf2[:, :, col0 + 2 * H:], prior[:, :, col0 + 2 * H:])
+
+
+def test_tower_residual_through_recurrence(cuda, monkeypatch):
+    """UnimodalNet.tower(..., merged) with the recurrences writing the residual sum themselves == the add_into pass."""
+    import mgr_b200 as mgr
+    net = mgr.UnimodalNet(20, 128, 22, 0.0, (0.5, 0.5, 0.5), seed=3).to(cuda)
+    B, T = 6, 10
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, T, 20, generator=g).to(cuda)
+    reg = net.sample_regularisers(B, T, seed=5, step=0, device=cuda, head=False)
+    outs = []
+    for aux in ("1", "0"):
+        monkeypatch.setenv("GR_TOWER_AUX", aux)
+        merged = torch.zeros(B, T, 256 + 16, device=cuda)
+        with torch.no_grad():
+            net.tower(x, reg, merged, 16)
+        outs.append(merged)
+    assert torch.equal(outs[0], outs[1])
