@@ -46,6 +46,21 @@ elif what == "a32":
     masks = ((torch.rand(8, BT // T + 1, F, device=dev) > 0.5).float() * 2)[:, :BT // T + 1].contiguous()
     for _ in range(2):
         layers._project(x, W, b, masks, BT // T, T, H)
+elif what == "a32full":       # speech layer-2 projection at the full benchmark batch
+    BT, T, F, H = 256000, 1000, 1000, 500
+    x = torch.randn(BT, F, device=dev); W = torch.randn(F, 8 * H, device=dev) * 0.05; b = torch.zeros(8 * H, device=dev)
+    masks = ((torch.rand(8, BT // T, F, device=dev) > 0.5).float() * 2).contiguous()
+    for _ in range(2):
+        layers._project(x, W, b, masks, BT // T, T, H, mask_scale=2.0)
+elif what == "small":         # fusion BLSTM(100) forward + backward at the benchmark batch
+    B, T, H = 256, 1000, 100
+    gates = torch.randn(B * T, 8 * H, device=dev) * 0.5
+    U = torch.randn(2, H, 4 * H, device=dev) / H ** 0.5
+    dy = torch.randn(B, T, 2 * H, device=dev)
+    for _ in range(2):
+        g2 = gates.clone()
+        y, c = ops.lstm_recurrence_fwd(g2, U, B, T, H, keep_cell=True)
+        ops.lstm_recurrence_bwd(g2, c, dy, U, B, T, H)
 elif what == "a32t":
     BT, T, F, H = 65536, 1000, 1600, 100
     x = torch.randn(BT, F, device=dev); dP = torch.randn(BT, 8 * H, device=dev)
