@@ -22,6 +22,7 @@
 // ~50 k cycles per tile on launch, TMEM allocation and per-thread-row stores (32 lines per warp
 // store instruction); see profiles/r01_gemm_a32_*.
 #include <stdlib.h>
+#include <string.h>
 #include "tc_common.cuh"
 
 namespace gr {
@@ -68,6 +69,27 @@ __device__ __forceinline__ void a32_tma_store_3d(const CUtensorMap* tm, const vo
                ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+__device__ __forceinline__ void a32_tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ void a32_tmem_ld_x64(uint32_t taddr, uint32_t (&v)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+      : "r"(taddr)
+      : "memory");
+}
+
 __device__ __forceinline__ void split2(float v, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat16 h = __float2bfloat16_rn(v);
   hi = __bfloat16_as_ushort(h);
@@ -110,6 +132,10 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tile_ring + kSchedDepth);
   // dropout-mask keep bits of the current / next k-block: [2 slots][4 variants x 2 sequences][4 words]
   uint32_t* kbits = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(tmem_ptr_s + 1) + 15) & ~uintptr_t(15));
+  // store-stream epilogue with the drain on the producer warps (epi_stg == 3): two 64 KB staging tiles
+  uint64_t* staged = reinterpret_cast<uint64_t*>(kbits + 64);   // [2] 128 epilogue threads filled the staging tile
+  uint64_t* drained = staged + 2;                                 // [2] the 8 producer warps wrote it to global memory
+  float* bias_s = reinterpret_cast<float*>(drained + 2);          // [256] the tile's bias slice (epi_stg == 3 only)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // tile decode (identical in every role): t -> (m0, var, n0, k-block range)
@@ -139,6 +165,7 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
     for (int s = 0; s < p.stages; ++s) { mbar_init(&fullA[s], 8); mbar_init(&fullB[s], 1); mbar_init(&empty[s], 1); }   // fullA: one arrival per producer warp
     for (int b = 0; b < 4; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
     for (int b = 0; b < kSchedDepth; ++b) { mbar_init(&sfull[b], 1); mbar_init(&sempty[b], 14); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&staged[b], 128); mbar_init(&drained[b], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -235,6 +262,42 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
     int it = 0;
     int gblk = 0;   // k-blocks handled so far (all tiles): slot parity of the keep-bit ring
     (void)gblk; (void)kbits;
+    // epi_stg == 3 (store-stream tiles): the producers have next to nothing to do (one k-block of K <= 64), so THEY write
+    // the staged output tiles to global memory -- warp w rows 16w .. 16w+15 of every 128-column chunk, 512 contiguous
+    // bytes per row -- one tile behind their own A tile, while the four epilogue warps only move TMEM -> staging.
+    int dcn = 0;                      // chunks drained so far (same sequence as the epilogue warps' counter)
+    int pm0 = 0, pvar = 0, pn0 = 0;   // the tile whose chunks are drained next
+    bool have_prev = false;
+    auto drain_tile = [&]() {
+      const int w = t >> 5;
+      const int cbase = pvar * p.Nv + pn0;
+      for (int c0 = 0; c0 < BN && pn0 + c0 < p.Nv; c0 += 128, ++dcn) {
+        const int db = dcn & 1;
+        mbar_wait(&staged[db], (uint32_t)((dcn >> 1) & 1));
+        const uint8_t* stg = epi + (size_t)db * 65536;
+        const bool cok = pn0 + c0 + 4 * lane < p.Nv && c0 + 4 * lane < BN;
+        const uint32_t q4l = (uint32_t)lane >> 3, jl = (uint32_t)lane & 7u;
+        const int nrow = min(16, p.M - pm0 - w * 16);
+        float* cptr = p.C + (size_t)(pm0 + w * 16) * p.ldc + cbase + c0 + 4 * lane;
+        const uint8_t* sbase = stg + (uint32_t)(w * 16) * 512u + q4l * 128u;
+        if (cok) {
+#pragma unroll 1
+          for (int i0 = 0; i0 < 16; i0 += 8) {
+            if (i0 >= nrow) break;
+            float4 o[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) o[u] = *reinterpret_cast<const float4*>(sbase + (uint32_t)(i0 + u) * 512u + ((jl ^ (uint32_t)u) << 4));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              if (i0 + u < nrow) *reinterpret_cast<float4*>(cptr) = o[u];
+              cptr += p.ldc;
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&drained[db])) : "memory");
+      }
+    };
     for (int tn = 0;; ++tn) {
     A32_NEXT_TILE(tn, tile)
     A32_TILE_DECODE(tile)
@@ -735,7 +798,16 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&fullA[s])) : "memory");
     }
     }
+    if constexpr (MODE == 1) {
+      if (p.epi_stg == 3) {           // (end of the tile's producer work) drain the PREVIOUS tile, remember this one
+        if (have_prev) drain_tile();
+        pm0 = m0; pvar = var; pn0 = n0; have_prev = true;
+      }
+    }
     }  // tile loop (producers)
+    if constexpr (MODE == 1) {
+      if (p.epi_stg == 3 && have_prev) drain_tile();
+    }
   } else if (warp < 14) {
     // =============== epilogue: 4 warps; warp q owns TMEM lanes (= tile rows) 32q..32q+31 ===============
     const int q = warp & 3;           // warps 10..13 -> 2, 3, 0, 1: any bijection onto the lane groups works
@@ -756,12 +828,52 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
       if (et == 0) A32_TRACE(14, lt);
       const int row = m0 + (int)r;
       const bool add_bias = p.bias != nullptr && z_ == 0;
-      if (p.epi_stg == 2) {
+      if (p.epi_stg == 3) {
+        // ---- store-stream epilogue, drain on the producer warps: these four warps move TMEM -> (+bias) -> one of two
+        // 64 KB swizzled staging tiles.  The tile's bias slice sits in shared memory (8 uniform global loads per 32
+        // columns had their L2 latency in every iteration) and the tcgen05.ld of the next 32 columns is in flight while
+        // the current ones are stored.
+        const int cbase = var * p.Nv + n0;
+        if (add_bias) {
+          asm volatile("bar.sync 2, 128;" ::: "memory");          // the previous tile's chunks have read bias_s
+          for (int c = et; c < BN; c += 128) bias_s[c] = (n0 + c < p.Nv) ? __ldg(p.bias + cbase + c) : 0.f;
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
+        for (int c0 = 0; c0 < BN && n0 + c0 < p.Nv; c0 += 128, ++cc) {
+          uint8_t* const stgw = epi + (size_t)(cc & 1) * 65536;
+          const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + c0);
+          // 64 columns per tcgen05.ld (a load + wait pair costs several hundred cycles whatever its width: x16 steps with
+          // the next load in flight were SLOWER than x32 steps, 11.5 k against 9.7 k cycles per tile)
+          const int ncols = min(128, min(BN - c0, p.Nv - n0 - c0));
+          mbar_wait(&drained[cc & 1], (uint32_t)(((cc >> 1) & 1) ^ 1));
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            if (64 * h >= ncols) break;
+            uint32_t v[64];
+            a32_tmem_ld_x64(tbase + (uint32_t)(64 * h), v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                     __uint_as_float(v[4 * j + 3]));
+              if (add_bias) {
+                const float4 bq = *reinterpret_cast<const float4*>(bias_s + c0 + 64 * h + 4 * j);
+                o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w;
+              }
+              // 32-column group 2h + j/8, 16-byte chunk j % 8 of its 128-byte row piece
+              *reinterpret_cast<float4*>(stgw + r * 512u + (uint32_t)(2 * h + (j >> 3)) * 128u +
+                                         ((((uint32_t)(j & 7)) ^ (r & 7u)) << 4)) = o;
+            }
+          }
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&staged[cc & 1])) : "memory");
+        }
+      } else if (p.epi_stg >= 2) {
         // ---- wide coalesced epilogue (store-stream tiles, one k-block; GR_A32_EPI=tma restores the tensor stores): 128
         // columns at a time through a 64 KB swizzled staging tile, then every warp instruction writes 512 contiguous
         // bytes of ONE output row (the 32-column TMA tensor stores write 128-byte row pieces).
         const int cbase = var * p.Nv + n0;
         for (int c0 = 0; c0 < BN && n0 + c0 < p.Nv; c0 += 128) {
+          uint8_t* const stgw = epi;
           asm volatile("bar.sync 2, 128;" ::: "memory");          // the previous drain has read the staging tile
 #pragma unroll 1
           for (int q4 = 0; q4 < 4; ++q4) {
@@ -799,7 +911,7 @@ gemm_a32_kernel(const __grid_constant__ CUtensorMap tmBh, const __grid_constant_
                 if (4 * j + 2 < ncol) o.z += brow[4 * j + 2];
                 if (4 * j + 3 < ncol) o.w += brow[4 * j + 3];
               }
-              *reinterpret_cast<float4*>(epi + r * 512u + (uint32_t)q4 * 128u + (((uint32_t)j ^ (r & 7u)) << 4)) = o;
+              *reinterpret_cast<float4*>(stgw + r * 512u + (uint32_t)q4 * 128u + (((uint32_t)j ^ (r & 7u)) << 4)) = o;
             }
           }
           asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -1079,7 +1191,7 @@ static int gemm_a32_launch(const float* A, int lda, int transA, int row_shift, c
   // operand stage is enough, the rest of shared memory keeps more TMA stores in flight
   p.epi_bufs = 2;
   { const char* es = getenv("GR_A32_EPI"); p.epi_stg = (es && es[0] == 's') ? 1 : 0; }
-  int stages = (int)((227 * 1024 - 1024 - 2 * kEpiStage - 384) / stage_bytes);
+  int stages = (int)((227 * 1024 - 1024 - 2 * kEpiStage - 768) / stage_bytes);
   if (stages > 4) stages = 4;
   if (p.kb_total == 1 && !p.use_atomic) {
     const char* eb = getenv("GR_A32_EPI_BUFS");
@@ -1090,15 +1202,19 @@ static int gemm_a32_launch(const float* A, int lda, int transA, int row_shift, c
     // Measured (profiles/r02_store_probe.txt): speech first layer 1.52 ms against 1.73 with the TMA tensor stores, skeletal
     // 1.10 against 1.13 -- still 2.7 TB/s of the 7.4 TB/s a plain fill reaches: 512-byte pieces of 128 rows, 16 KB apart
     { const char* es = getenv("GR_A32_EPI");
-      if (p.nvg == 1 && !(es && (es[0] == 't' || es[0] == 's'))) { p.epi_stg = 2; p.epi_bufs = 4; } }
-    while (p.epi_bufs > 2 && 1024 + stage_bytes + (size_t)p.epi_bufs * kEpiStage + 512 > 227 * 1024) p.epi_bufs -= 2;
+      if (p.nvg == 1 && !(es && (es[0] == 't' || es[0] == 's'))) { p.epi_stg = 2; p.epi_bufs = 4; }
+      // two staging tiles drained by the producer warps (row-major fast producer only); GR_A32_EPI=wide1: one tile,
+      // drained by the epilogue warps themselves
+      if (p.epi_stg == 2 && mode == 1 && !(es && strcmp(es, "wide1") == 0) &&
+          1024 + stage_bytes + (size_t)8 * kEpiStage + 2048 <= 227 * 1024) { p.epi_stg = 3; p.epi_bufs = 8; } }
+    while (p.epi_stg != 3 && p.epi_bufs > 2 && 1024 + stage_bytes + (size_t)p.epi_bufs * kEpiStage + 512 > 227 * 1024) p.epi_bufs -= 2;
     if (p.epi_stg == 2 && p.epi_bufs < 4) p.epi_stg = 0;   // no room for the 64 KB staging tile: TMA stores
     if (1024 + stage_bytes + (size_t)p.epi_bufs * kEpiStage + 512 > 227 * 1024) return set_error(GR_EUNSUPPORTED, "gemm_a32: tile does not fit shared memory");
   } else
   if (stages < 2) return set_error(GR_EUNSUPPORTED, "gemm_a32: tile does not fit shared memory");
   p.stages = stages;
   p.tmem_cols = 512;   // two accumulators of <= 256 columns
-  const size_t smem = 1024 + stages * stage_bytes + (size_t)p.epi_bufs * kEpiStage + (3 * stages + 8 + 2 * kSchedDepth) * 8 + kSchedDepth * 4 + 16 + 16 + 256;
+  const size_t smem = 1024 + stages * stage_bytes + (size_t)p.epi_bufs * kEpiStage + (3 * stages + 8 + 2 * kSchedDepth) * 8 + kSchedDepth * 4 + 16 + 16 + 256 + 32 + (p.epi_stg == 3 ? 1024 : 0);
   CUtensorMap tBh, tBl, tC;
   int rc;
   if ((rc = make_map(&tBh, b_hi, (uint64_t)nvar * Nv, ldb, ldb, p.BN)) != GR_OK) return rc;

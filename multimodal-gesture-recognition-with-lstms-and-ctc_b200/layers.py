@@ -18,6 +18,7 @@ from torch import nn
 from . import ops
 
 GEMM_PASSES = 3  # bf16x3 (fp32-faithful) tensor-core projections; 1 = plain bf16
+BIAS_COLUMN = __import__("os").environ.get("GR_BIAS_COLUMN", "1") != "0"   # see _project
 
 
 def _project(x2, W, b, masks, B, T, H, passes=3, mask_scale=0.0):
@@ -26,6 +27,24 @@ def _project(x2, W, b, masks, B, T, H, passes=3, mask_scale=0.0):
     `mask_scale` > 0: the masks are dropout masks with values in {0, mask_scale}."""
     BT, F = x2.shape
     gates = torch.empty((BT, 8 * H), dtype=torch.float32, device=x2.device)
+    if b is not None and BIAS_COLUMN and H > 128 and F + 1 <= 64:
+        # Narrow first layers (K = 39 / 20: ONE k-block, a pure store stream of B*T x 8H floats): the bias rides in the
+        # k-block's padding -- a column of ones appended to x, the bias as the matching row of W -- so the store-bound
+        # epilogue has nothing to add (1.0 * (b_hi + b_lo) reproduces b to 2^-17 relative).  H > 128 keeps the call on
+        # the one-variant-per-CTA schedule, where the mask is a plain multiply (its ones-column stays 1).
+        Fp = (F + 1 + 3) // 4 * 4
+        xp = torch.nn.functional.pad(x2, (0, Fp - F))
+        xp[:, F] = 1.0
+        Wp = torch.zeros((Fp, 8 * H), dtype=torch.float32, device=W.device)
+        Wp[:F] = W
+        Wp[F] = b
+        mp = None if masks is None else torch.nn.functional.pad(masks, (0, Fp - F), value=1.0)
+        wt_hi, wt_lo = ops.split_bf16(Wp, transpose=True)
+        if mp is None:
+            ops.gemm_a32(xp, wt_hi, wt_lo, BT, 8 * H, Fp, gates, 8 * H)
+        else:
+            ops.gemm_a32(xp, wt_hi, wt_lo, BT, H, Fp, gates, 8 * H, nvar=8, mask=mp, rows_per_seq=T)
+        return gates
     wt_hi, wt_lo = ops.split_bf16(W, transpose=True)  # (8H, pad8(F)): B operand, K-major
     if F % 4:
         # 39 MFCC / odd feature counts: zero-pad the (small) input to 16-byte rows so that the
