@@ -133,6 +133,9 @@ int gr_lstm_recurrence_fwd_f32(float* gates, const float* U, int B, int T, int H
  * Only the tensor-memory kernel of the wide layers has this output: gr_lstm_recurrence_aux_supported(B, H) != 0,
  * else GR_EUNSUPPORTED.  aux, ld_aux and H must keep 16-byte alignment. */
 int gr_lstm_recurrence_aux_supported(int B, int H);
+/* CTAs (= SMs held for the whole launch) of the tensor-memory recurrence kernels for this shape, 0 when another
+ * kernel would run (narrow layers, unsupported H).  Lets the host decide whether two half-batch launches fit side by side. */
+int gr_lstm_recurrence_grid(int B, int H);
 int gr_lstm_recurrence_fwd_aux_f32(float* gates, const float* U, int B, int T, int H, float* y, float* cell,
                                    float* aux, int ld_aux, int accumulate, void* workspace,
                                    size_t workspace_bytes, void* stream);

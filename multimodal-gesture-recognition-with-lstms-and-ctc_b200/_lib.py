@@ -42,6 +42,7 @@ _SIGNATURES = {
     "gr_lstm_workspace_bytes": ([c_int, c_int, ctypes.POINTER(c_size_t)], c_int),
     "gr_lstm_recurrence_fwd_f32": ([_P, _P, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P], c_int),
     "gr_lstm_recurrence_aux_supported": ([c_int, c_int], c_int),
+    "gr_lstm_recurrence_grid": ([c_int, c_int], c_int),
     "gr_lstm_recurrence_fwd_aux_f32": ([_P, _P, c_int, c_int, c_int, _P, _P, _P, c_int, c_int, _P, c_size_t, _P], c_int),
     "gr_lstm_recurrence_bwd_f32": ([_P, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P], c_int),
     "gr_gemm_bf16x3_f32": ([_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P],

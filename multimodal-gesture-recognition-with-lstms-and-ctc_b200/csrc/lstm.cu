@@ -286,6 +286,7 @@ int lstm_fwd_tc_launch(float* gates, const float* U, int B, int T, int H, float*
 bool lstm_tcu_supported(int B, int H);
 size_t lstm_tcu_workspace_bytes(int B, int H);
 size_t lstm_tcu_trace_offset(int B, int H);
+int lstm_tcu_grid(int B, int H);
 int lstm_fwd_tcu_launch(float* gates, const float* U, int B, int T, int H, float* y, float* cell, void* workspace,
                         cudaStream_t s, float* aux = nullptr, int ld_aux = 0, int aux_mode = 0);
 
@@ -386,6 +387,11 @@ extern "C" int gr_lstm_recurrence_fwd_f32(float* gates, const float* U, int B, i
   void* args[] = {&p};
   GR_CUDA(cudaLaunchCooperativeKernel((void*)lstm_fwd_kernel, dim3(2 * p.UG), dim3(kLstmThreads), args, smem, s));
   return GR_OK;
+}
+
+extern "C" int gr_lstm_recurrence_grid(int B, int H) {
+  if (B <= 0 || H <= 0 || gr::lstm_small_supported(H) || !gr::use_tcu_path(B, H)) return 0;
+  return gr::lstm_tcu_grid(B, H);
 }
 
 extern "C" int gr_lstm_recurrence_aux_supported(int B, int H) {

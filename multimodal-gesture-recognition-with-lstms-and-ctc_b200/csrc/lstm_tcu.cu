@@ -965,6 +965,7 @@ static TcuLayout tcu_layout(int B, int H) {
 }
 
 size_t lstm_tcu_workspace_bytes(int B, int H) { return tcu_layout(B, H).total; }
+int lstm_tcu_grid(int B, int H) { TcuLayout L = tcu_layout(B, H); return 2 * L.NSB * L.UGn; }
 size_t lstm_tcu_trace_offset(int B, int H) { return tcu_layout(B, H).off_trace; }
 
 bool lstm_tcu_supported(int B, int H) {

@@ -11,6 +11,8 @@ skeletal_lstm_ctc.py:309-331, multimodal_fusion/multimodal.py:159-168): (B,T,F) 
 (4H), bwd kernel, bwd recurrent, bwd bias], gate order i,f,c,o, `.trainable` for freezing
 (multimodal.py:33-55).  `DenseSoftmax` mirrors Dense(C)+Activation('softmax') (speech:86-90).
 """
+import os
+
 import numpy as np
 import torch
 from torch import nn
@@ -18,7 +20,7 @@ from torch import nn
 from . import ops
 
 GEMM_PASSES = 3  # bf16x3 (fp32-faithful) tensor-core projections; 1 = plain bf16
-BIAS_COLUMN = __import__("os").environ.get("GR_BIAS_COLUMN", "1") != "0"   # see _project
+BIAS_COLUMN = os.environ.get("GR_BIAS_COLUMN", "1") != "0"   # see _project
 
 
 def _project(x2, W, b, masks, B, T, H, passes=3, mask_scale=0.0):
@@ -62,6 +64,59 @@ def _project(x2, W, b, masks, B, T, H, passes=3, mask_scale=0.0):
     return gates
 
 
+_SIDE = {}   # device -> two side streams for half-batch recurrences
+
+
+def _halves(B, H, device):
+    """Training recurrences of a layer hold grid(B,H) SMs (38 at H=300, 64 at H=500) for T dependent steps while the rest
+    of the GPU idles -- nothing else of a uni-modal training step can run beside them.  When two half-batch launches fit
+    side by side they run on two streams: each half's step is shorter (smaller tiles) and both proceed concurrently
+    (config-2 layer, fwd + BPTT: 8.33 -> 7.05 ms).  Results are bit-identical (rows are independent).  None = do not split."""
+    if os.environ.get("GR_TRAIN_SPLIT", "1") == "0" or B < 64 or B % 2:
+        return None
+    g = ops.lstm_recurrence_grid(B // 2, H)
+    if g <= 0 or 2 * g > torch.cuda.get_device_properties(device).multi_processor_count:
+        return None
+    if device not in _SIDE:
+        _SIDE[device] = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+    return _SIDE[device]
+
+
+def _recurrence_fwd_train(gates, U, B, T, H):
+    """Forward recurrence keeping gates / cell for BPTT -> (y, cell); two concurrent half batches when they fit."""
+    side = _halves(B, H, gates.device)
+    if side is None:
+        return ops.lstm_recurrence_fwd(gates, U, B, T, H, keep_cell=True)
+    y = torch.empty((B, T, 2 * H), dtype=torch.float32, device=gates.device)
+    cell = torch.empty((B, T, 2 * H), dtype=torch.float32, device=gates.device)
+    cur, h = torch.cuda.current_stream(), B // 2
+    for i, s_ in enumerate(side):
+        s_.wait_stream(cur)
+        with torch.cuda.stream(s_):
+            ops.lstm_recurrence_fwd(gates[i * h * T:(i + 1) * h * T], U, h, T, H, keep_cell=True, y=y[i * h:(i + 1) * h],
+                                    cell=cell[i * h:(i + 1) * h])
+    for s_ in side:
+        cur.wait_stream(s_)
+    return y, cell
+
+
+def _recurrence_bwd(gates, cell, dy, U, B, T, H):
+    """BPTT in place over `gates` -> dP (B*T, 8H); two concurrent half batches when they fit."""
+    side = _halves(B, H, gates.device)
+    dy = dy.contiguous()
+    if side is None:
+        return ops.lstm_recurrence_bwd(gates, cell, dy, U, B, T, H).reshape(B * T, 8 * H)
+    cur, h = torch.cuda.current_stream(), B // 2
+    g2 = gates.reshape(B * T, 8 * H)
+    for i, s_ in enumerate(side):
+        s_.wait_stream(cur)
+        with torch.cuda.stream(s_):
+            ops.lstm_recurrence_bwd(g2[i * h * T:(i + 1) * h * T], cell[i * h:(i + 1) * h], dy[i * h:(i + 1) * h], U, h, T, H)
+    for s_ in side:
+        cur.wait_stream(s_)
+    return g2
+
+
 class _BlstmFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, W, U, b, masks, passes, mask_scale=0.0):
@@ -73,7 +128,10 @@ class _BlstmFn(torch.autograd.Function):
         x2 = x.reshape(B * T, F)
         need_grad = any(ctx.needs_input_grad[:4])
         gates = _project(x2, W, b, masks, B, T, H, mask_scale=mask_scale)
-        y, cell = ops.lstm_recurrence_fwd(gates, U, B, T, H, keep_cell=need_grad)
+        if need_grad:
+            y, cell = _recurrence_fwd_train(gates, U, B, T, H)
+        else:
+            y, cell = ops.lstm_recurrence_fwd(gates, U, B, T, H, keep_cell=False)
         ctx.mask_scale = mask_scale
         if need_grad:
             ctx.save_for_backward(x, W, U, masks, gates, cell, y)
@@ -85,7 +143,7 @@ class _BlstmFn(torch.autograd.Function):
         B, T, F = x.shape
         H = U.shape[1]
         BT = B * T
-        dP = ops.lstm_recurrence_bwd(gates, cell, dy.contiguous(), U, B, T, H).reshape(BT, 8 * H)
+        dP = _recurrence_bwd(gates, cell, dy, U, B, T, H)
         x2 = x.reshape(BT, F)
         y2 = y.reshape(BT, 2 * H)
         db = ops.colsum(dP) if ctx.needs_input_grad[3] else None

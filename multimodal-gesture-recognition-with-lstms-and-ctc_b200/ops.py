@@ -169,18 +169,27 @@ def lstm_workspace(B, H, device):
     return _workspace("lstm", nbytes.value, device)
 
 
+def lstm_recurrence_grid(B, H):
+    """CTAs of the tensor-memory recurrence for this shape (0: another kernel runs)."""
+    return int(_lib.load().gr_lstm_recurrence_grid(int(B), int(H)))
+
+
 def lstm_aux_supported(B, H):
     """True when the recurrence of this shape can write / accumulate h into an auxiliary (B,T,ld) buffer."""
     return bool(_lib.load().gr_lstm_recurrence_aux_supported(int(B), int(H)))
 
 
-def lstm_recurrence_fwd(gates, U, B, T, H, keep_cell=True, aux=None, aux_col0=0, aux_accumulate=False, want_y=True):
+def lstm_recurrence_fwd(gates, U, B, T, H, keep_cell=True, aux=None, aux_col0=0, aux_accumulate=False, want_y=True,
+                        y=None, cell=None):
     """`aux`: (B, T, Fo) buffer whose columns [aux_col0, aux_col0 + 2H) also receive h (stored, or added when
-    `aux_accumulate`); with `want_y=False` no separate y tensor is written (returns y = None)."""
+    `aux_accumulate`); with `want_y=False` no separate y tensor is written (returns y = None).  `y` / `cell`:
+    caller-provided contiguous (B,T,2H) outputs (e.g. the two halves of one tensor)."""
     import ctypes
-    require_cuda(gates, U, aux)
-    y = torch.empty((B, T, 2 * H), dtype=torch.float32, device=gates.device) if (want_y or aux is None) else None
-    cell = torch.empty((B, T, 2 * H), dtype=torch.float32, device=gates.device) if keep_cell else None
+    require_cuda(gates, U, aux, y, cell)
+    if y is None:
+        y = torch.empty((B, T, 2 * H), dtype=torch.float32, device=gates.device) if (want_y or aux is None) else None
+    if cell is None:
+        cell = torch.empty((B, T, 2 * H), dtype=torch.float32, device=gates.device) if keep_cell else None
     ws = lstm_workspace(B, H, gates.device)
     # algorithmic bytes (SURVEY 8d): read 4H pre-activations, write h (+ 4H gates + c when kept)
     _lib.note_work(float(B) * T * 2 * H * (40 if keep_cell else 20))

@@ -268,3 +268,30 @@ def test_tower_residual_through_recurrence(cuda, monkeypatch):
             net.tower(x, reg, merged, 16)
         outs.append(merged)
     assert torch.equal(outs[0], outs[1])
+
+
+def test_training_recurrence_half_batches_bit_equal(cuda, monkeypatch):
+    """layers._recurrence_fwd_train / _recurrence_bwd: two concurrent half-batch launches (GR_TRAIN_SPLIT, default for
+    B >= 64 on the tensor-memory kernels) give bit-identical y, cell, dP and weight gradients to the single launch."""
+    import mgr_b200 as mgr
+    from mgr_b200 import layers, ops
+    B, T, F, H = 64, 14, 40, 128
+    if ops.lstm_recurrence_grid(B // 2, H) <= 0:
+        pytest.skip("tensor-memory recurrence not available")
+    layer = mgr.BidirectionalLSTM(F, H, dropout=0.5, seed=11).to(cuda)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, T, F, generator=g).to(cuda)
+    masks = ((torch.rand(8, B, F, generator=g) > 0.5).float() * 2).to(cuda)
+    dy = torch.randn(B, T, 2 * H, generator=g).to(cuda)
+    res = []
+    for split in ("1", "0"):
+        monkeypatch.setenv("GR_TRAIN_SPLIT", split)
+        assert (layers._halves(B, H, x.device) is not None) == (split == "1")
+        xi = x.clone().requires_grad_(True)
+        y = layer(xi, masks, True)
+        gr_ = torch.autograd.grad(y, [xi, layer.kernel, layer.recurrent_kernel, layer.bias], grad_outputs=dy)
+        res.append((y.detach(),) + tuple(gr_))
+    assert torch.equal(res[0][0], res[1][0])          # y
+    assert torch.equal(res[0][1], res[1][1])          # dx (no atomics on this path)
+    for a, b in zip(res[0][2:], res[1][2:]):          # dW / dU / db: split-K atomics -> fp32 summation order may differ
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6 * float(b.abs().max()))
