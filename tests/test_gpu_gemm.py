@@ -72,7 +72,8 @@ def test_row_shift_split(cuda):
 @pytest.mark.parametrize("BT,T,F,H,nvar", [(96, 12, 64, 32, 8), (200, 25, 39, 20, 8), (384, 48, 1600, 100, 8),
                                            (300, 30, 20, 300, 1), (256, 16, 1000, 500, 8),
                                            (1000, 200, 1600, 100, 8), (768, 128, 40, 500, 8), (1300, 650, 600, 300, 8),
-                                           (900, 300, 1000, 500, 1)])
+                                           (900, 300, 1000, 500, 1), (1000, 200, 40, 300, 8), (333, 111, 24, 500, 8),
+                                           (520, 130, 64, 150, 1)])
 @pytest.mark.parametrize("mask_scale", [0.0, 2.0])
 def test_fused_prologue_projection(cuda, BT, T, F, H, nvar, mask_scale):
     """gr_gemm_a32_f32, transA=0: P[:, v*H:(v+1)*H] = (X o mask_v) W_v + b with X read as fp32.
