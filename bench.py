@@ -588,13 +588,27 @@ def run_gpu(args):
         # algorithmic bytes of the recurrence per launch, both directions:
         # read 4H pre-activations + write h (+ 4H gates + c when kept for BPTT) per (b, t, unit)
         calls = _lib.kernel_timing_shapes.get(dom, [])
-        tot_bytes = sum(c for c in calls) / max(1, len(calls))
-        avg_ms = per_kernel[dom]["avg_ms"]
-        ach = tot_bytes / (avg_ms * 1e-3) / 1e9
+        # The entry point is launched on several layer shapes per step (speech / skeletal towers, fusion layer).  The
+        # roofline is stated for ONE launch shape -- the group of launches with equal algorithmic bytes that takes the most
+        # time (the speech-tower layers; the shape of the committed ncu capture behind `traffic`) -- and the average over
+        # all launches of the entry point is kept beside it.
+        groups = {}
+        for b_, t_ in zip(calls, ktimes[dom]):
+            groups.setdefault(b_, []).append(t_)
+        gb, gt = max(groups.items(), key=lambda kv: sum(kv[1]))
+        avg_ms = sum(gt) / len(gt)
+        ach = gb / (avg_ms * 1e-3) / 1e9
+        all_bytes = sum(c for c in calls) / max(1, len(calls))
+        all_ms = per_kernel[dom]["avg_ms"]
         roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": ach / hbm_peak, "traffic": read_traffic(dom), "traffic_capture": read_traffic_shape(dom),
                     "peak_kind": peak_kind,
-                    "avg_launch_ms": avg_ms, "share_of_step": per_kernel[dom]["ms_per_step"] / serial_ms,
+                    "avg_launch_ms": avg_ms, "launches_of_this_shape_per_step": len(gt) / serial_steps,
+                    "algorithmic_bytes_per_launch": gb,
+                    "all_launches": {"avg_launch_ms": all_ms, "achieved": all_bytes / (all_ms * 1e-3) / 1e9,
+                                     "frac": all_bytes / (all_ms * 1e-3) / 1e9 / hbm_peak,
+                                     "launches_per_step": per_kernel[dom]["launches_per_step"]},
+                    "share_of_step": per_kernel[dom]["ms_per_step"] / serial_ms,
                     "serial_step_ms": serial_ms,
                     "note": "durations from serial steps run right after the timed region (kernel alone on the GPU); "
                             "algorithmic bytes = 20 B (inference) / 40 B (training) per (b,t,unit,dir); the kernel is "

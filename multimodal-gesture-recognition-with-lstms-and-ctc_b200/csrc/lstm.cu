@@ -364,9 +364,18 @@ extern "C" int gr_lstm_recurrence_fwd_f32(float* gates, const float* U, int B, i
   size_t need = 0;
   gr_lstm_workspace_bytes(B, H, &need);
   if (workspace_bytes < need) return set_error(GR_EWORKSPACE, "lstm_fwd: workspace too small");
-  if (use_small_path(H, gates, nullptr, nullptr))
+  // Narrow layers (H <= 104) at a large batch: the register-resident kernel needs one CTA per 4 sequences (128 SMs for
+  // 2.2 ms at B = 256, H = 100 = 280 SM-ms), the tensor-memory kernel 2 x ceil(H/16) CTAs per 256 sequences (14 SMs for
+  // 6.4 ms = 89 SM-ms).  The fusion step is bound by the sum of its kernels' SM-time, not by this layer's latency, so the
+  // FORWARD pass of such a layer goes to the tensor-memory kernel from B = 256 on: 42.2 -> 40.5 ms per step on the same box
+  // (profiles/r02_narrow_layer_on_tcu.txt; the BPTT kernel does not pay off: 11.8 ms on 14 SMs, 6.5 on 28).
+  // GR_LSTM_NARROW_FWD=small|tcu forces the choice (tcu from B = 128 on); GR_LSTM_IMPL overrides everything.
+  const char* nf = getenv("GR_LSTM_NARROW_FWD");
+  const bool narrow_tcu = !(nf && nf[0] == 's') && B >= ((nf && nf[0] == 't') ? 128 : 256) && !getenv("GR_LSTM_IMPL") &&
+                          lstm_small_supported(H) && lstm_tcu_supported(B, H);
+  if (!narrow_tcu && use_small_path(H, gates, nullptr, nullptr))
     return lstm_small_run(false, gates, U, B, T, H, y, cell, nullptr, static_cast<cudaStream_t>(stream));
-  if (use_tcu_path(B, H))
+  if (narrow_tcu || use_tcu_path(B, H))
     return lstm_fwd_tcu_launch(gates, U, B, T, H, y, cell, workspace, static_cast<cudaStream_t>(stream));
   if (use_tc_path(B, H))
     return lstm_fwd_tc_launch(gates, U, B, T, H, y, cell, workspace, static_cast<cudaStream_t>(stream));
@@ -424,9 +433,11 @@ extern "C" int gr_lstm_recurrence_bwd_f32(float* gates, const float* cell, const
   size_t need = 0;
   gr_lstm_workspace_bytes(B, H, &need);
   if (workspace_bytes < need) return set_error(GR_EWORKSPACE, "lstm_bwd: workspace too small");
-  if (use_small_path(H, gates, cell, dy))
+  const char* nbw = getenv("GR_LSTM_NARROW_BWD");
+  const bool narrow_tcu = nbw && nbw[0] == 't' && B >= 128 && !getenv("GR_LSTM_IMPL") && lstm_tcu_bwd_supported(B, H);
+  if (!narrow_tcu && use_small_path(H, gates, cell, dy))
     return lstm_small_run(true, gates, U, B, T, H, nullptr, const_cast<float*>(cell), dy, static_cast<cudaStream_t>(stream));
-  if (use_tcu_bwd_path(B, H))
+  if (narrow_tcu || use_tcu_bwd_path(B, H))
     return lstm_bwd_tcu_launch(gates, cell, dy, U, B, T, H, workspace, static_cast<cudaStream_t>(stream));
   LstmBwdParams p;
   lstm_config(B, H, &p.HS, &p.UG, &p.Bp);

@@ -1052,6 +1052,10 @@ static TcuBwdLayout tcu_bwd_layout(int B, int H) {
   TcuBwdLayout L;
   int nb = 16;
   while (nb < 128 && 2 * nb < B) nb *= 2;
+  if (const char* e = getenv("GR_TCU_BWD_NB")) {   // experiments: force the tile width
+    const int v = atoi(e);
+    if (v == 16 || v == 32 || v == 64 || v == 128) nb = v;
+  }
   L.NB = nb;
   L.NTg = (B + nb - 1) / nb;
   L.NSB = (L.NTg + 1) / 2;

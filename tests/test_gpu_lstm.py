@@ -295,3 +295,25 @@ def test_training_recurrence_half_batches_bit_equal(cuda, monkeypatch):
     assert torch.equal(res[0][1], res[1][1])          # dx (no atomics on this path)
     for a, b in zip(res[0][2:], res[1][2:]):          # dW / dU / db: split-K atomics -> fp32 summation order may differ
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-6 * float(b.abs().max()))
+
+
+def test_narrow_layer_large_batch_forward_kernel_choice(cuda, monkeypatch):
+    """H <= 104 at B >= 256 (the fusion BLSTM(100) of the benchmark step): the forward pass runs on the tensor-memory kernel
+    by default; same y / saved state as the register-resident kernel within fp32 noise, and BPTT (register-resident kernel)
+    on the state either one saved gives the same dP."""
+    from mgr_b200 import ops
+    B, T, H = 256, 11, 100
+    g = torch.Generator().manual_seed(77)
+    P = (torch.randn(B * T, 8 * H, generator=g) * 0.6).to(cuda)
+    U = (torch.randn(2, H, 4 * H, generator=g) / H ** 0.5).to(cuda)
+    dy = (torch.randn(B, T, 2 * H, generator=g) * 0.1).to(cuda)
+    out = {}
+    for choice in ("default", "small"):
+        if choice == "small":
+            monkeypatch.setenv("GR_LSTM_NARROW_FWD", "small")
+        gt = P.clone()
+        y, cell = ops.lstm_recurrence_fwd(gt, U, B, T, H, keep_cell=True)
+        dP = ops.lstm_recurrence_bwd(gt.clone(), cell, dy, U, B, T, H)
+        out[choice] = (y, cell, gt, dP)
+    for a, b, tol in zip(out["default"], out["small"], (2e-5, 2e-5, 2e-5, 2e-5)):
+        assert (a - b).abs().max().item() <= tol * max(1.0, float(b.abs().max()))
