@@ -471,6 +471,10 @@ def run_gpu(args):
     pmode = os.environ.get("GR_PIPELINE", "1")
     pipeline = pmode in ("1", "2", "3")
     trainer.hook_after_towers = pmode != "3"
+    # towers `depth` batches ahead (FusionTrainer's prefetch queue).  Measured at N = 1: depth 2 / 3 = 39.95-40.23 ms per
+    # step against 39.45-39.9 for depth 1 -- a second set of independent tower kernels does not pack any better, so the
+    # default stays 1 (GR_PREFETCH_DEPTH for experiments)
+    depth = int(os.environ.get("GR_PREFETCH_DEPTH", "1")) if pipeline else 0
 
     def train_step(xa, xs, lab, il, ll, nxt=None, nxt_ready=None):
         return trainer.step((xa, xs, lab, il, ll), next_inputs=nxt if pipeline else None, next_ready=nxt_ready)
@@ -500,14 +504,15 @@ def run_gpu(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    ahead = [(xa_d, xs_d)] * max(depth, 1)
     for _ in range(max(args.warmup, args.min_warmup)):
-        train_step(xa_d, xs_d, lab_d, il_d, ll_d, (xa_d, xs_d))
+        train_step(xa_d, xs_d, lab_d, il_d, ll_d, ahead)
     launches0 = _lib.launch_count
     _lib.kernel_timing_begin(["gr_lstm_recurrence_fwd_f32", "gr_lstm_recurrence_bwd_f32", "gr_gemm_bf16x3_f32",
                               "gr_ctc_loss_grad_f32", "gr_split_bf16_f32", "gr_gemm_a32_f32"])
     sampler.mark("begin")
     # every timed step trains one batch and enqueues the towers of the next one (K tower passes + K fusion passes)
-    total_ms = timed(lambda: train_step(xa_d, xs_d, lab_d, il_d, ll_d, (xa_d, xs_d)), args.steps)
+    total_ms = timed(lambda: train_step(xa_d, xs_d, lab_d, il_d, ll_d, ahead), args.steps)
     sampler.mark("end")
     ktimes = _lib.kernel_timing_end()
     launches = _lib.launch_count - launches0
@@ -525,20 +530,23 @@ def run_gpu(args):
             ev = copy_stream.record_event()
         return ts, ev
 
-    staged = [h2d()]
+    trainer.close()                      # the device-resident arm's prefetches are for other tensors
+    staged = [h2d() for _ in range(max(depth, 1))]
 
     def e2e_step():
         # one H2D copy of a full batch from pinned memory (on a copy stream) and one D2H read of the loss per step;
-        # with the pipeline the copy made in step n is the batch of step n+1, whose towers start as soon as it lands
-        (cur, ev) = staged[0]
+        # with the pipeline the copy made in step n is the batch of step n+depth, whose towers start as soon as it lands
+        (cur, ev) = staged.pop(0)
         torch.cuda.current_stream().wait_event(ev)
         for t in cur:
             t.record_stream(torch.cuda.current_stream())
-        staged[0] = h2d() if pipeline else (cur, ev)
-        nxt, nev = staged[0]
-        loss = train_step(*cur, nxt=(nxt[0], nxt[1]), nxt_ready=nev)
-        if not pipeline:
-            staged[0] = h2d()
+        if pipeline:
+            staged.append(h2d())
+            nxt = [(b_[0], b_[1]) for b_, _ in staged]
+            loss = train_step(*cur, nxt=nxt, nxt_ready=[e_ for _, e_ in staged])
+        else:
+            loss = train_step(*cur)
+            staged.append(h2d())
         losses.append(loss.cpu())
 
     if args.skip_e2e:

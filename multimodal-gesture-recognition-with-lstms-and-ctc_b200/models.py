@@ -315,34 +315,66 @@ class FusionTrainer:
         # kernels -- DESIGN 5.  The next fusion step needs those towers anyway, so the wait is off the critical path.
         self.hook_after_towers = hook_after_towers
         self.step_no = 0                  # next step to be trained
-        self._pending = None              # (step index, reg, towers handle)
+        self._queue = []                  # prefetched towers, oldest first: (step index, reg, towers handle)
+
+    @property
+    def _pending(self):                   # (the next step's prefetch, if any; kept for introspection / tests)
+        return self._queue[0] if self._queue else None
 
     def _launch(self, xa, xs, step, ready=None):
         B, T = xa.shape[0], xa.shape[1]
         reg = self.model.sample_regularisers(B, T, seed=self.seed, step=step, device=xa.device)
         return step, reg, self.model.launch_towers(xa, xs, reg, ready)
 
+    @staticmethod
+    def _matches(entry, step, xa, xs):
+        ins = entry[2].get("inputs", (None, None))
+        return entry[0] == step and ins[0] is xa and ins[1] is xs
+
     def step(self, batch, next_inputs=None, next_ready=None):
-        """Train on `batch`; `next_inputs` = (xa, xs) of the following batch (its towers are enqueued now),
-        `next_ready` = CUDA event after which those tensors are valid (e.g. recorded on a copy stream)."""
+        """Train on `batch`; `next_inputs` = (xa, xs) of the following batch (its towers are enqueued now), or a LIST of
+        the following batches in order (towers two or more batches ahead: more independent work to fill the SMs with;
+        single-GPU only -- with a gradient hook every prefetched tower is joined before the collective);
+        `next_ready` = CUDA event after which the LAST of those tensors is valid (e.g. recorded on a copy stream), or a
+        list with one event (or None) per announced batch."""
         xa, xs, labels, il, ll = batch
-        pend = self._pending
-        self._pending = None
-        if pend is None or pend[0] != self.step_no or pend[2].get("inputs", (None, None))[0] is not xa \
-                or pend[2]["inputs"][1] is not xs:
+        if next_inputs is None:
+            upcoming = []
+        elif not isinstance(next_inputs[0], (tuple, list)):
+            upcoming = [next_inputs]
+        else:
+            upcoming = list(next_inputs)
+        q = self._queue
+        if not q or not self._matches(q[0], self.step_no, xa, xs):
             # cold start, or the prefetch was for other tensors.  A stale prefetch is JOINED before it is dropped:
             # its `merged` / regulariser buffers were allocated on this stream while the side streams still work on
             # them; releasing them un-joined would hand the blocks back to this stream's allocator pool mid-flight.
-            self._drain(pend)
-            pend = self._launch(xa, xs, self.step_no)
-        _, reg, towers = pend
-        if next_inputs is not None:
-            self._pending = self._launch(next_inputs[0], next_inputs[1], self.step_no + 1, next_ready)
+            self._drain_all()
+            q = self._queue = [self._launch(xa, xs, self.step_no)]
+        # keep what is still valid of the prefetches beyond the head, (re)launch the rest
+        for i, (nxa, nxs) in enumerate(upcoming):
+            idx = self.step_no + 1 + i
+            if len(q) > i + 1 and self._matches(q[i + 1], idx, nxa, nxs):
+                continue
+            for stale in q[i + 1:]:
+                self._drain(stale)
+            del q[i + 1:]
+            if isinstance(next_ready, (tuple, list)):
+                ready = next_ready[i]
+            else:
+                ready = next_ready if i == len(upcoming) - 1 else None
+            q.append(self._launch(nxa, nxs, idx, ready))
+        if len(q) > len(upcoming) + 1:      # prefetches for batches that are no longer announced
+            for stale in q[len(upcoming) + 1:]:
+                self._drain(stale)
+            del q[len(upcoming) + 1:]
+        _, reg, towers = q.pop(0)
         loss, grads = self.model.loss_and_grads(xa, xs, labels, il, ll, reg, global_batch=self.global_batch,
                                                 towers=towers)
         if self.grad_hook is not None:
-            if self.hook_after_towers and self._pending is not None:
-                self.model.join_towers(self._pending[2])
+            if self.hook_after_towers:
+                for pend in q:
+                    self.model.join_towers(pend[2])
             grads = self.grad_hook(grads)
         self.opt.step(grads)
         self.step_no += 1
@@ -352,10 +384,14 @@ class FusionTrainer:
         if pend is not None:
             self.model.join_towers(pend[2])
 
+    def _drain_all(self):
+        q, self._queue = self._queue, []
+        for pend in q:
+            self._drain(pend)
+
     def close(self):
-        """Join a prefetch that will never be consumed (last `next_inputs` of an epoch) before its buffers go."""
-        pend, self._pending = self._pending, None
-        self._drain(pend)
+        """Join prefetches that will never be consumed (last `next_inputs` of an epoch) before their buffers go."""
+        self._drain_all()
 
     def __del__(self):
         try:

@@ -111,3 +111,38 @@ def test_hook_can_be_ordered_after_the_prefetched_towers():
     joins = [i for i, e in enumerate(m.log) if e[0] == "join"]
     assert joins and m.log[joins[-1]][1] == id(b[0])          # the calling stream joined batch b's towers ...
     assert order[0][1] == joins[-1] + 1                        # ... right before the hook ran
+
+
+def test_two_batches_ahead_queue():
+    """next_inputs as a LIST: towers of batches n+1 and n+2 are in flight while batch n trains; each is launched once,
+    in order, consumed with its own regularisers; with a gradient hook every prefetch is joined before the hook."""
+    calls = []
+    t, m, o = _trainer(hook=lambda g: (calls.append(len(m.log)), g)[1])
+    bs = [(_T(), _T()) for _ in range(5)]
+    for n in range(5):
+        nxt = [bs[k] for k in (n + 1, n + 2) if k < 5]
+        assert t.step(bs[n] + (0, 0, 0), next_inputs=nxt or None, next_ready="ev") == n
+    towers = [e[1] for e in m.log if e[0] == "towers"]
+    assert towers == [0, 1, 2, 3, 4]                      # every batch's towers launched exactly once, in order
+    fus = [e[1] for e in m.log if e[0] == "fusion"]
+    assert fus == [0, 1, 2, 3, 4]
+    # step 0: towers 0, 1, 2 are enqueued before fusion 0
+    first_fusion = m.log.index(("fusion", 0, id(bs[0][0])))
+    assert [e[1] for e in m.log[:first_fusion] if e[0] == "towers"] == [0, 1, 2]
+    # the hook of step 0 ran after BOTH outstanding prefetches were joined
+    joins_before_hook0 = [e for e in m.log[first_fusion:calls[0]] if e[0] == "join"]
+    assert [j[1] for j in joins_before_hook0] == [id(bs[1][0]), id(bs[2][0])]
+    t.close()
+
+
+def test_queue_drops_stale_prefetches():
+    t, m, _ = _trainer()
+    a, b, c, d = [(_T(), _T()) for _ in range(4)]
+    t.step(a + (0, 0, 0), next_inputs=[b, c])
+    n0 = len(m.log)
+    t.step(b + (0, 0, 0), next_inputs=[d])              # c was announced for step 2 but d comes instead
+    tail = m.log[n0:]
+    assert ("join", id(c[0])) in tail                      # the stale prefetch is joined before it is dropped
+    assert [e[1] for e in tail if e[0] == "towers"] == [2] and [e[2] for e in tail if e[0] == "towers"] == [id(d[0])]
+    t.step(d + (0, 0, 0))
+    assert [e[1] for e in m.log if e[0] == "fusion"] == [0, 1, 2]
