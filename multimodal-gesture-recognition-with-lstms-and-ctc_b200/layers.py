@@ -279,8 +279,7 @@ class BidirectionalLSTM(nn.Module):
     def forward(self, x, masks=None, dropout_masks=False):
         """`dropout_masks=True`: `masks` came from `make_masks` / `ops.dropout_mask` with this layer's rate, i.e. every
         element is 0 or 1/(1-rate) (injected masks with other values must leave it False)."""
-        scale = 1.0 / (1.0 - self.dropout) if (dropout_masks and masks is not None and 0.0 < self.dropout < 1.0) else 0.0
-        return blstm(x, self.kernel, self.recurrent_kernel, self.bias, masks, mask_scale=scale)
+        return blstm(x, self.kernel, self.recurrent_kernel, self.bias, masks, mask_scale=self._scale(masks, dropout_masks))
 
 
 class _DenseSoftmaxFn(torch.autograd.Function):
